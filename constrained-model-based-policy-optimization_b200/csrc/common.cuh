@@ -1,0 +1,88 @@
+// Shared declarations of libcmbpo_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cmbpo_b200.h"
+
+#define CMBPO_MAX_LAYERS 8
+#define CMBPO_MAX_E 8        // members held in registers by the per-row math
+#define CMBPO_MAX_OBS 64     // per-row register arrays
+#define CMBPO_MAX_ACT 32
+
+void cmbpo_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            cmbpo_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                   \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+
+#define CMBPO_CHECK(cond, ...)           \
+    do {                                 \
+        if (!(cond)) {                   \
+            cmbpo_set_error(__VA_ARGS__); \
+            return 1;                    \
+        }                                \
+    } while (0)
+
+// One MLP ensemble resident in HBM.  fp32 master copy in the reference's layout
+// (fc.py:135-139: W [E,in,out], b [E,out]) + pre-packed 16-bit tiles for the tcgen05 path.
+struct Net {
+    bool loaded = false;
+    int E = 0, n_layers = 0;
+    int dims[CMBPO_MAX_LAYERS + 1] = {0};
+    int acts[CMBPO_MAX_LAYERS] = {0};
+    float* W[CMBPO_MAX_LAYERS] = {nullptr};
+    float* b[CMBPO_MAX_LAYERS] = {nullptr};
+    bool probabilistic = false;
+    int D = 0;                  // output width seen by callers (half the last layer if probabilistic)
+    bool has_in = false, has_out = false;
+    float *mu_in = nullptr, *sig_in = nullptr;                       // [in]; sigma = max(sqrt(var),1e-2)
+    float *mu_out = nullptr, *sig_out = nullptr, *l2s_out = nullptr; // [D]; l2s = 2*log(sigma)
+    int n_elite = 0;
+    int* elite = nullptr;       // device [n_elite]
+    // tcgen05 path: weights packed as ready-to-copy shared-memory tile images (see ens_tc.cu)
+    void* tc_pack[3] = {nullptr, nullptr, nullptr};   // per precision (index = CMBPO_PREC_*)
+    size_t tc_pack_bytes[3] = {0, 0, 0};
+    float* tc_bias = nullptr;   // biases re-laid for the epilogue
+};
+
+struct Workspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct cmbpo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    Net nets[CMBPO_NET_COUNT];
+    float* log_std = nullptr;   // [A]
+    int A = 0;
+    Workspace ws[8];            // reusable scratch slots
+    int64_t launches = 0;
+};
+
+// grow-only scratch
+int cmbpo_ws_get(cmbpo_ctx* ctx, int slot, size_t bytes, void** out);
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- internal entry points shared between translation units -------------------------------
+// fp32 CUDA-core MLP chain: X [N,in] (or [E,N,in]) -> raw last-layer output [E,N,dims[L]]
+int ens_forward_f32(cmbpo_ctx* ctx, const Net& net, const float* x, int64_t N, bool x_is_3d,
+                    float* out_raw);
+// tcgen05 MLP chain (2 hidden layers), same contract
+int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* out_raw,
+                   int precision);
+bool ens_tc_supported(const Net& net);
+int ens_forward(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, bool x_is_3d, float* out_raw,
+                int precision);

@@ -1,0 +1,488 @@
+// Step-wise model rollout (policy -> dynamics ensemble -> FakeEnv row math -> sampler rules ->
+// ModelBuffer write-out) and the single-step entry points cmbpo_policy_act / cmbpo_fakeenv_step.
+//
+// The GEMM chains go through ens_forward(precision): fp32 CUDA cores (logic reference on the
+// device) or the tcgen05 kernels of ens_tc.cu.  The per-row arithmetic lives in row_math.cuh and
+// is shared with the fully fused kernel.
+//
+// Reference: samplers/model_sampler.py:239-375 (sample), 377-416 (_finish_paths),
+//            models/fake_env.py:66-172, buffers/modelbuffer.py:114-135 (store_multiple),
+//            policies/cpo_policy.py:801-835.
+#include "common.cuh"
+#include "row_math.cuh"
+
+namespace {
+
+struct ValueHead {            // one non-probabilistic value ensemble read through PE.predict
+    const float* raw;         // [E, N, 1]
+    int E;
+    const float *mu_out, *sig_out;   // [1] or null
+};
+
+__device__ __forceinline__ float value_of(const ValueHead& h, int64_t N, int64_t p) {
+    // tf.reduce_mean over members of inverse_transform(out) (pe.py:343, pens/utils.py:167)
+    float s = 0.f;
+    for (int e = 0; e < h.E; ++e) {
+        float m = h.raw[(int64_t)e * N + p];
+        if (h.mu_out) m = __fadd_rn(__fmul_rn(h.sig_out[0], m), h.mu_out[0]);
+        s = (e == 0) ? m : __fadd_rn(s, m);
+    }
+    return __fdiv_rn(s, (float)h.E);
+}
+
+struct PolicyRowsArgs {
+    int64_t N;                 // rows
+    int O, A;
+    const float* obs;          // [N,O]
+    const float* mu_raw;       // [N,A] actor output
+    const float* log_std;      // [A]
+    ValueHead v, vc;
+    const float* eps;          // [N,A] or null
+    const int32_t* path_ids;   // [N] or null
+    int64_t path_base;
+    uint64_t seed;
+    int step;
+    const uint8_t* alive;      // [N] or null (all rows)
+    // outputs
+    float *pi, *logp, *mu, *vout, *vcout;   // [N,A],[N],[N,A],[N],[N]; any may be null
+    float* xin;                // [N, O+A] concat(obs, pi) or null
+    // pending bootstraps (rollout only)
+    uint8_t* pending;          // [N] bit0: last_val, bit1: last_cval
+    float *last_val, *last_cval;
+};
+
+__global__ void policy_rows_kernel(PolicyRowsArgs a) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.N) return;
+    const float v = value_of(a.v, a.N, p), vc = value_of(a.vc, a.N, p);
+    if (a.pending) {
+        uint8_t f = a.pending[p];
+        if (f) {                                   // model_sampler.py:401-407 on s_{t+1}
+            if (f & 1) a.last_val[p] = v;
+            if (f & 2) a.last_cval[p] = vc;
+            a.pending[p] = 0;
+        }
+    }
+    if (a.alive && !a.alive[p]) return;
+    if (a.vout) a.vout[p] = v;
+    if (a.vcout) a.vcout[p] = vc;
+    if (!a.mu_raw) return;
+    float mu[CMBPO_MAX_ACT], eps[CMBPO_MAX_ACT], pi[CMBPO_MAX_ACT];
+    const int64_t gid = a.path_ids ? (int64_t)a.path_ids[p] : a.path_base + p;
+    for (int i = 0; i < a.A; ++i) {
+        mu[i] = a.mu_raw[p * a.A + i];
+        eps[i] = a.eps ? a.eps[p * a.A + i] : philox_normal(a.seed, gid, a.step, RNG_STREAM_ACT, i);
+    }
+    float lp = actor_row(mu, a.log_std, eps, a.A, pi);
+    if (a.logp) a.logp[p] = lp;
+    for (int i = 0; i < a.A; ++i) {
+        if (a.pi) a.pi[p * a.A + i] = pi[i];
+        if (a.mu) a.mu[p * a.A + i] = mu[i];
+        if (a.xin) a.xin[p * (a.O + a.A) + a.O + i] = pi[i];
+    }
+    if (a.xin) for (int o = 0; o < a.O; ++o) a.xin[p * (a.O + a.A) + o] = a.obs[p * a.O + o];
+}
+
+struct RawDyn {
+    const float* raw; int64_t N; int W; int64_t p;
+    __device__ float operator()(int e, int c) const { return raw[((int64_t)e * N + p) * W + c]; }
+};
+
+// ---- single-step FakeEnv.step ------------------------------------------------------------
+struct EnvStepArgs {
+    int64_t N; int O, A;
+    EnvRowCfg c; int n_elite;
+    const float* obs; const float* raw;   // raw [E,N,2D]
+    const int32_t* elite_pos; const float* state_eps; const int32_t* path_ids;
+    uint64_t seed; int step;
+    float *next_obs, *rew, *cost; uint8_t* term; float *dkl_path, *ep_var;
+    double* dkl_sum;   // 1 double accumulator
+};
+
+__global__ void env_step_kernel(EnvStepArgs a) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double dk = 0.0;
+    if (p < a.N) {
+        float obs[CMBPO_MAX_OBS], nx[CMBPO_MAX_OBS];
+        for (int o = 0; o < a.O; ++o) obs[o] = a.obs[p * a.O + o];
+        const int64_t gid = a.path_ids ? (int64_t)a.path_ids[p] : p;
+        int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, gid, a.step, a.n_elite);
+        float seps[CMBPO_MAX_OBS];
+        const float* sp = nullptr;
+        if (!a.c.deterministic && a.state_eps) {
+            for (int o = 0; o < a.O; ++o) seps[o] = a.state_eps[p * a.O + o];
+            sp = seps;
+        }
+        RawDyn raw{a.raw, a.N, 2 * a.c.D, p};
+        EnvRowOut r = fakeenv_row(a.c, raw, obs, pos, sp, nx, a.ep_var ? a.ep_var + p * a.O : nullptr);
+        for (int o = 0; o < a.O; ++o) a.next_obs[p * a.O + o] = nx[o];
+        a.rew[p] = r.rew; a.cost[p] = r.cost; a.term[p] = r.term ? 1 : 0;
+        a.dkl_path[p] = r.dkl_path;
+        dk = (double)r.dkl_path;
+    }
+    // ensemble_dkl_mean (fake_env.py:114): block partial -> one atomic per block
+    for (int o = 16; o > 0; o >>= 1) dk += __shfl_down_sync(0xffffffffu, dk, o);
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dk;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[w];
+        atomicAdd(a.dkl_sum, s);
+    }
+}
+
+__global__ void finish_mean_kernel(const double* sum, int64_t n, float* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (float)(sum[0] / (double)n);
+}
+
+// ---- rollout step ------------------------------------------------------------------------
+struct StepArgs {
+    int64_t B; int O, A, T, t; int last_storable;   // last_storable = T-2: storing it ends the path (horizon)
+    EnvRowCfg c; int n_elite;
+    int uncertainty; double dkl_lim;
+    int64_t path_base; uint64_t seed;
+    const float* raw;        // [E,B,2D]
+    float* cur_obs;          // [B,O] in/out
+    uint8_t* alive;          // [B]
+    uint8_t* pending;        // [B]
+    const float *pi, *mu, *logp, *v, *vc;      // this step's policy outputs [B,..]
+    const int32_t* elite_pos;                  // [B] slice for this step or null
+    const float* state_eps;                    // [B,O] slice or null
+    cmbpo_rollout_bufs b;
+};
+
+__global__ void rollout_step_kernel(StepArgs a) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double fed = 0, dsum = 0, stored = 0, evsum = 0;
+    if (p < a.B && a.alive[p]) {
+        const int O = a.O, A = a.A, t = a.t;
+        float obs[CMBPO_MAX_OBS], nx[CMBPO_MAX_OBS], seps[CMBPO_MAX_OBS];
+        for (int o = 0; o < O; ++o) obs[o] = a.cur_obs[p * O + o];
+        const int64_t gid = a.path_base + p;
+        int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, gid, t, a.n_elite);
+        const float* sp = nullptr;
+        if (!a.c.deterministic) {
+            for (int o = 0; o < O; ++o)
+                seps[o] = a.state_eps ? a.state_eps[p * O + o]
+                                      : philox_normal(a.seed, gid, t, RNG_STREAM_STATE, o);
+            sp = seps;
+        }
+        RawDyn raw{a.raw, a.B, 2 * a.c.D, p};
+        EnvRowOut r = fakeenv_row(a.c, raw, obs, pos, sp, nx, nullptr);
+        fed = 1; dsum = (double)r.dkl_path;
+        const float v = a.v[p], vc = a.vc[p];
+        // uncertainty cut-off BEFORE the step is stored (model_sampler.py:275-290)
+        const double next_dkl = a.b.cum_dkl[p] + (double)r.dkl_path;
+        if (a.uncertainty && next_dkl >= a.dkl_lim) {
+            a.alive[p] = 0;
+            a.b.end_reason[p] = CMBPO_END_UNCERTAIN;
+            a.b.last_val[p] = v; a.b.last_cval[p] = vc;      // V(s_t), VC(s_t): model_sampler.py:401-407
+        } else {
+            // ModelBuffer.store_multiple (modelbuffer.py:114-135), time-major
+            const int64_t row = (int64_t)t * a.B + p;
+            for (int o = 0; o < O; ++o) { a.b.obs[row * O + o] = obs[o]; a.b.nextobs[row * O + o] = nx[o]; }
+            for (int i = 0; i < A; ++i) { a.b.act[row * A + i] = a.pi[p * A + i]; a.b.mu[row * A + i] = a.mu[p * A + i]; }
+            a.b.rew[row] = r.rew; a.b.val[row] = v; a.b.cost[row] = r.cost; a.b.cval[row] = vc;
+            a.b.logp[row] = a.logp[p]; a.b.dyn_error[row] = r.ep_var_mean; a.b.dkl[row] = r.dkl_path;
+            a.b.term[row] = r.term ? 1 : 0;
+            a.b.length[p] = t + 1;
+            a.b.cum_dkl[p] = next_dkl;                       // model_sampler.py:332
+            a.b.path_return[p] += (double)r.rew;             // :317-318
+            a.b.path_cost[p] += (double)r.cost;
+            stored = 1; evsum = (double)r.ep_var_sum;
+            for (int o = 0; o < O; ++o) a.cur_obs[p * O + o] = nx[o];   // :350
+            if (t >= a.last_storable) {                      // path_length >= max_path_length-1 (:352)
+                a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_HORIZON; a.pending[p] = 3;
+            } else if (r.term) {                             // env terminal (:357-364): V boot 0, VC boot VC(s')
+                a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_TERMINAL;
+                a.b.last_val[p] = 0.f; a.pending[p] = 2;
+            }
+        }
+    }
+    // per-step statistics: rows fed, sum dkl, rows stored, sum ep_var
+    double vals[4] = {fed, dsum, stored, evsum};
+    __shared__ double sh[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double x = vals[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
+        if (s != 0.0) atomicAdd(a.b.step_stats + (int64_t)a.t * 4 + threadIdx.x, s);
+    }
+}
+
+__global__ void rollout_init_kernel(int64_t B, int O, const float* start, float* cur, uint8_t* alive,
+                                    uint8_t* pending, cmbpo_rollout_bufs b) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    for (int o = 0; o < O; ++o) cur[p * O + o] = start[p * O + o];
+    alive[p] = 1; pending[p] = 0;
+    b.length[p] = 0; b.end_reason[p] = CMBPO_END_ALIVE;
+    b.last_val[p] = 0.f; b.last_cval[p] = 0.f;
+    b.cum_dkl[p] = 0.0; b.path_return[p] = 0.0; b.path_cost[p] = 0.0;
+}
+
+// paths still alive when the step budget ran out keep END_ALIVE; their bootstrap values are
+// V(s_now), VC(s_now) so that finish_all_paths (model_sampler.py:418-444) is a no-op on the device
+__global__ void rollout_final_kernel(int64_t B, int O, const float* cur, const uint8_t* alive,
+                                     cmbpo_rollout_bufs b, const float* v, const float* vc) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    if (alive[p]) { b.last_val[p] = v[p]; b.last_cval[p] = vc[p]; }
+    if (b.final_obs) for (int o = 0; o < O; ++o) b.final_obs[p * O + o] = cur[p * O + o];
+}
+
+EnvRowCfg make_env_cfg(const Net& dyn, const cmbpo_env_cfg& e, int O) {
+    EnvRowCfg c;
+    c.O = O; c.D = dyn.D; c.E = dyn.E;
+    c.term_id = e.term_id; c.cost_id = e.cost_id; c.predicts_cost = e.predicts_cost;
+    c.deterministic = e.deterministic; c.predicts_delta = e.predicts_delta;
+    c.sig_out = dyn.sig_out; c.mu_out = dyn.mu_out; c.l2s_out = dyn.l2s_out; c.elite = dyn.elite;
+    return c;
+}
+
+ValueHead make_head(const Net& n, const float* raw) {
+    ValueHead h;
+    h.raw = raw; h.E = n.E;
+    h.mu_out = n.has_out ? n.mu_out : nullptr; h.sig_out = n.sig_out;
+    return h;
+}
+
+int check_dyn(const cmbpo_ctx* ctx, const cmbpo_env_cfg* cfg, int O) {
+    const Net& dyn = ctx->nets[CMBPO_NET_DYN];
+    CMBPO_CHECK(dyn.loaded && dyn.probabilistic, "dynamics ensemble not loaded (or not probabilistic)");
+    CMBPO_CHECK(dyn.has_out, "dynamics ensemble needs an output scaler");
+    CMBPO_CHECK(dyn.E <= CMBPO_MAX_E, "at most %d ensemble members", CMBPO_MAX_E);
+    CMBPO_CHECK(O <= CMBPO_MAX_OBS, "obs dim %d > %d", O, CMBPO_MAX_OBS);
+    CMBPO_CHECK(dyn.D == O + 1 + (cfg->predicts_cost ? 1 : 0), "model output width %d does not match obs dim %d", dyn.D, O);
+    CMBPO_CHECK(dyn.n_elite > 0, "no elite indices");
+    return 0;
+}
+
+// policy forward for N rows: actor MLP + V + VC chains, then the row kernel
+int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precision) {
+    Net& actor = ctx->nets[CMBPO_NET_ACTOR];
+    Net& v = ctx->nets[CMBPO_NET_V];
+    Net& vc = ctx->nets[CMBPO_NET_VC];
+    CMBPO_CHECK(v.loaded && vc.loaded, "value ensembles not loaded");
+    float *raw_v, *raw_vc, *raw_mu = nullptr;
+    if (cmbpo_ws_get(ctx, 3, (size_t)(v.E + vc.E) * a.N * sizeof(float), (void**)&raw_v)) return 1;
+    raw_vc = raw_v + (size_t)v.E * a.N;
+    // small nets: tcgen05 path only if supported, else fp32
+    int pv = (precision != CMBPO_PREC_FP32 && ens_tc_supported(v)) ? precision : CMBPO_PREC_FP32;
+    if (ens_forward(ctx, v, a.obs, a.N, false, raw_v, pv)) return 1;
+    if (ens_forward(ctx, vc, a.obs, a.N, false, raw_vc, pv)) return 1;
+    if (with_actor) {
+        CMBPO_CHECK(actor.loaded && ctx->log_std, "actor not loaded");
+        CMBPO_CHECK(a.A <= CMBPO_MAX_ACT, "act dim too large");
+        if (cmbpo_ws_get(ctx, 4, (size_t)a.N * a.A * sizeof(float), (void**)&raw_mu)) return 1;
+        int pa = (precision != CMBPO_PREC_FP32 && ens_tc_supported(actor)) ? precision : CMBPO_PREC_FP32;
+        if (ens_forward(ctx, actor, a.obs, a.N, false, raw_mu, pa)) return 1;
+    }
+    a.mu_raw = raw_mu; a.log_std = ctx->log_std;
+    a.v = make_head(v, raw_v); a.vc = make_head(vc, raw_vc);
+    policy_rows_kernel<<<cdiv(a.N, 128), 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int cmbpo_policy_act(cmbpo_ctx* ctx, const float* obs, int64_t N, const float* eps,
+                                const int32_t* path_ids, uint64_t seed, int step, float* pi,
+                                float* logp, float* mu, float* v, float* vc, int precision) {
+    CMBPO_CHECK(ctx, "null context");
+    if (N <= 0) return 0;
+    Net& actor = ctx->nets[CMBPO_NET_ACTOR];
+    const bool with_actor = (pi != nullptr || mu != nullptr || logp != nullptr);
+    PolicyRowsArgs a = {};
+    a.N = N; a.O = ctx->nets[CMBPO_NET_V].dims[0]; a.A = with_actor ? actor.dims[actor.n_layers] : 0;
+    a.obs = obs; a.eps = eps; a.path_ids = path_ids; a.path_base = 0; a.seed = seed; a.step = step;
+    a.pi = pi; a.logp = logp; a.mu = mu; a.vout = v; a.vcout = vc;
+    return policy_forward(ctx, a, with_actor, precision);
+}
+
+extern "C" int cmbpo_fakeenv_step(cmbpo_ctx* ctx, const cmbpo_env_cfg* cfg, const float* obs,
+                                  const float* act, int64_t N, const int32_t* elite_pos,
+                                  const float* state_eps, const int32_t* path_ids, uint64_t seed,
+                                  int step, float* next_obs, float* rew, float* cost, uint8_t* term,
+                                  float* dkl_path, float* ep_var, float* dkl_mean_out, int precision) {
+    CMBPO_CHECK(ctx && cfg, "null argument");
+    if (N <= 0) return 0;
+    Net& dyn = ctx->nets[CMBPO_NET_DYN];
+    CMBPO_CHECK(dyn.loaded, "dynamics ensemble not loaded");
+    const int Din = dyn.dims[0];
+    const int O = dyn.D - 1 - (cfg->predicts_cost ? 1 : 0), A = Din - O;
+    if (check_dyn(ctx, cfg, O)) return 1;
+    // concat(obs, act) (fake_env.py:81)
+    float *xin, *raw;
+    double* dsum;
+    if (cmbpo_ws_get(ctx, 4, (size_t)N * Din * sizeof(float) + 64, (void**)&xin)) return 1;
+    dsum = (double*)((char*)xin + (((size_t)N * Din * sizeof(float) + 15) / 16) * 16);
+    CUDA_TRY(cudaMemcpy2DAsync(xin, Din * sizeof(float), obs, O * sizeof(float), O * sizeof(float), N,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(xin + O, Din * sizeof(float), act, A * sizeof(float), A * sizeof(float),
+                               N, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(dsum, 0, sizeof(double), ctx->stream));
+    if (cmbpo_ws_get(ctx, 2, (size_t)dyn.E * N * 2 * dyn.D * sizeof(float), (void**)&raw)) return 1;
+    if (ens_forward(ctx, dyn, xin, N, false, raw, precision)) return 1;
+    EnvStepArgs a = {};
+    a.N = N; a.O = O; a.A = A; a.c = make_env_cfg(dyn, *cfg, O); a.n_elite = dyn.n_elite;
+    a.obs = obs; a.raw = raw; a.elite_pos = elite_pos; a.state_eps = state_eps; a.path_ids = path_ids;
+    a.seed = seed; a.step = step;
+    a.next_obs = next_obs; a.rew = rew; a.cost = cost; a.term = term; a.dkl_path = dkl_path;
+    a.ep_var = ep_var; a.dkl_sum = dsum;
+    env_step_kernel<<<cdiv(N, 128), 128, 0, ctx->stream>>>(a);
+    if (dkl_mean_out) finish_mean_kernel<<<1, 32, 0, ctx->stream>>>(dsum, N, dkl_mean_out);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const cmbpo_rollout_bufs* bufs) {
+    CMBPO_CHECK(ctx && cfg && bufs, "null argument");
+    const int64_t B = cfg->B;
+    if (B <= 0) return 0;
+    Net& dyn = ctx->nets[CMBPO_NET_DYN];
+    Net& actor = ctx->nets[CMBPO_NET_ACTOR];
+    CMBPO_CHECK(dyn.loaded && actor.loaded, "networks not loaded");
+    const int Din = dyn.dims[0];
+    const int A = actor.dims[actor.n_layers], O = Din - A;
+    if (check_dyn(ctx, &cfg->env, O)) return 1;
+    const int T = cfg->T;
+    CMBPO_CHECK(T >= 2, "max_path_length must be >= 2");
+    const int n_steps = (cfg->max_steps > 0 && cfg->max_steps < T - 1) ? cfg->max_steps : T - 1;
+
+    float *cur, *pi, *mu, *logp, *v, *vc, *xin, *raw;
+    uint8_t *alive, *pending;
+    size_t fl = (size_t)B * (O + 2 * A + 3 + Din);
+    char* base;
+    if (cmbpo_ws_get(ctx, 5, fl * sizeof(float) + 2 * (size_t)B + 256, (void**)&base)) return 1;
+    cur = (float*)base; pi = cur + (size_t)B * O; mu = pi + (size_t)B * A; logp = mu + (size_t)B * A;
+    v = logp + B; vc = v + B; xin = vc + B;
+    alive = (uint8_t*)(xin + (size_t)B * Din); pending = alive + B;
+    if (cmbpo_ws_get(ctx, 2, (size_t)dyn.E * B * 2 * dyn.D * sizeof(float), (void**)&raw)) return 1;
+
+    CUDA_TRY(cudaMemsetAsync(bufs->step_stats, 0, (size_t)T * 4 * sizeof(double), ctx->stream));
+    rollout_init_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, O, bufs->start_obs, cur, alive, pending, *bufs);
+    ctx->launches++;
+
+    for (int t = 0; t <= n_steps; ++t) {
+        const bool last = (t == n_steps);
+        PolicyRowsArgs pa = {};
+        pa.N = B; pa.O = O; pa.A = A; pa.obs = cur;
+        pa.eps = (bufs->act_eps && !last) ? bufs->act_eps + (size_t)t * B * A : nullptr;
+        pa.path_base = cfg->path_id_base; pa.seed = cfg->seed; pa.step = t;
+        pa.alive = alive; pa.pi = pi; pa.logp = logp; pa.mu = mu; pa.vout = v; pa.vcout = vc;
+        pa.xin = xin; pa.pending = pending; pa.last_val = bufs->last_val; pa.last_cval = bufs->last_cval;
+        if (policy_forward(ctx, pa, !last, cfg->precision)) return 1;
+        if (last) break;
+        if (ens_forward(ctx, dyn, xin, B, false, raw, cfg->precision)) return 1;
+        StepArgs sa = {};
+        sa.B = B; sa.O = O; sa.A = A; sa.T = T; sa.t = t; sa.last_storable = T - 2;
+        sa.c = make_env_cfg(dyn, cfg->env, O); sa.n_elite = dyn.n_elite;
+        sa.uncertainty = cfg->uncertainty_mode; sa.dkl_lim = cfg->dkl_lim;
+        sa.path_base = cfg->path_id_base; sa.seed = cfg->seed;
+        sa.raw = raw; sa.cur_obs = cur; sa.alive = alive; sa.pending = pending;
+        sa.pi = pi; sa.mu = mu; sa.logp = logp; sa.v = v; sa.vc = vc;
+        sa.elite_pos = bufs->elite_pos ? bufs->elite_pos + (size_t)t * B : nullptr;
+        sa.state_eps = bufs->state_eps ? bufs->state_eps + (size_t)t * B * O : nullptr;
+        sa.b = *bufs;
+        rollout_step_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(sa);
+        ctx->launches++;
+    }
+    rollout_final_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, O, cur, alive, *bufs, v, vc);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- batch-global truncation --------------------------------------------------------------
+namespace {
+
+__global__ void hist_kernel(const int32_t* length, const uint8_t* reason, int64_t B, int T,
+                            unsigned long long* hist) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < B;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        int L = length[p];
+        if (L < 0) L = 0;
+        if (L > T) L = T;
+        atomicAdd(hist + L, 1ull);
+        if (reason[p] == CMBPO_END_UNCERTAIN) atomicAdd(hist + (T + 1) + L, 1ull);
+    }
+}
+
+__global__ void cap_flags_kernel(const int32_t* length, int64_t B, int cap_step, int32_t* flags) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < B) flags[p] = length[p] > cap_step ? 1 : 0;
+}
+
+// close path p at step s with V(s_s), VC(s_s) = val[s][p], cval[s][p]
+__device__ __forceinline__ void cut_path(const cmbpo_rollout_bufs& b, int64_t B, int64_t p, int s,
+                                         int reason) {
+    b.length[p] = s;
+    b.end_reason[p] = (uint8_t)reason;
+    b.last_val[p] = b.val[(int64_t)s * B + p];
+    b.last_cval[p] = b.cval[(int64_t)s * B + p];
+}
+
+__global__ void cap_apply_kernel(cmbpo_rollout_bufs b, int64_t B, int cap_step, int64_t cap_n,
+                                 const int64_t* rank) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    if (b.length[p] > cap_step && rank[p] < cap_n) cut_path(b, B, p, cap_step, CMBPO_END_CAPPED);
+}
+
+__global__ void stop_apply_kernel(cmbpo_rollout_bufs b, int64_t B, int stop_step) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    if (b.length[p] > stop_step + 1) cut_path(b, B, p, stop_step + 1, CMBPO_END_STOPPED);
+}
+
+}  // namespace
+
+extern "C" int cmbpo_rollout_histogram(cmbpo_ctx* ctx, const int32_t* length, const uint8_t* end_reason,
+                                       int64_t B, int T, int64_t* hist_host) {
+    CMBPO_CHECK(ctx && hist_host, "null argument");
+    unsigned long long* d;
+    size_t bytes = 2 * (size_t)(T + 1) * sizeof(unsigned long long);
+    if (cmbpo_ws_get(ctx, 6, bytes, (void**)&d)) return 1;
+    CUDA_TRY(cudaMemsetAsync(d, 0, bytes, ctx->stream));
+    hist_kernel<<<max(1, min(ctx->sm_count * 4, cdiv(B, 256))), 256, 0, ctx->stream>>>(length, end_reason, B, T, d);
+    ctx->launches++;
+    CUDA_TRY(cudaMemcpyAsync(hist_host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int cmbpo_rollout_truncate(cmbpo_ctx* ctx, const cmbpo_rollout_bufs* bufs, int64_t B, int T,
+                                      int cap_step, int64_t cap_n, int stop_step) {
+    CMBPO_CHECK(ctx && bufs, "null argument");
+    (void)T;
+    if (cap_step >= 0 && cap_n > 0) {
+        int32_t* flags;
+        int64_t* rank;
+        char* base;
+        if (cmbpo_ws_get(ctx, 4, (size_t)B * 4 + (size_t)(B + 1) * 8 + 64, (void**)&base)) return 1;
+        rank = (int64_t*)base;
+        flags = (int32_t*)(base + (size_t)(B + 1) * 8);
+        cap_flags_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(bufs->length, B, cap_step, flags);
+        ctx->launches++;
+        if (cmbpo_path_offsets(ctx, flags, B, rank)) return 1;
+        cap_apply_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(*bufs, B, cap_step, cap_n, rank);
+        ctx->launches++;
+    }
+    if (stop_step >= 0) {
+        stop_apply_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(*bufs, B, stop_step);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,242 @@
+// Per-row arithmetic of the rollout step, shared by the fp32 CUDA-core path and the fused
+// tcgen05 path so that both apply exactly the same logic (the precision of the GEMM chain is
+// the only thing that differs between them).
+//
+// Everything here follows the reference's op order in float32 without FMA contraction
+// (__fmul_rn / __fadd_rn), because numpy/TF evaluate these expressions one ufunc at a time.
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Counter = (path id lo, path id hi, step, stream<<16|block),
+// key = seed.  Keyed by GLOBAL path id so results do not depend on how paths are sharded.
+// ------------------------------------------------------------------------------------------
+enum { RNG_STREAM_ACT = 0, RNG_STREAM_ELITE = 1, RNG_STREAM_STATE = 2 };
+
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// two standard normals from two uint32 (Box-Muller on (u+0.5)/2^32)
+__device__ inline void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;
+    float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
+    u1 = fminf(u1, 0.99999994f);
+    float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// the k-th standard normal of (path, step, stream)
+__device__ inline float philox_normal(uint64_t seed, int64_t path, int step, int stream, int k) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)path, (uint32_t)((uint64_t)path >> 32), (uint32_t)step,
+                  ((uint32_t)stream << 16) | (uint32_t)(k >> 2), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), o);
+    float z0, z1;
+    if ((k & 3) < 2) box_muller(o[0], o[1], z0, z1); else box_muller(o[2], o[3], z0, z1);
+    return (k & 1) ? z1 : z0;
+}
+
+// uniform elite position in [0, n_elite): what np.random.choice(elite_inds, N) draws (fake_env.py:176)
+__device__ inline int philox_elite_pos(uint64_t seed, int64_t path, int step, int n_elite) {
+    uint32_t o[4];
+    philox4x32_10((uint32_t)path, (uint32_t)((uint64_t)path >> 32), (uint32_t)step,
+                  ((uint32_t)RNG_STREAM_ELITE << 16), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    return (int)(((uint64_t)o[0] * (uint64_t)n_elite) >> 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// numpy's float32 pairwise sum for n < 128 contiguous elements (np.mean over the last axis):
+// 8 running partial sums, a fixed combination tree, then the n%8 tail added sequentially.
+// ------------------------------------------------------------------------------------------
+// exact numpy order over an array already in registers / local memory
+template <int MAXN>
+__device__ inline float np_sum_f32(const float (&a)[MAXN], int n) {
+    if (n < 8) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, a[i]);
+        return s;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n & 7); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    }
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) s = __fadd_rn(s, a[i]);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// models/statics.py
+// ------------------------------------------------------------------------------------------
+// antsafe "notdone" with the precedence exactly as written (statics.py:24-27): the boolean
+// health flags multiply z_rot before the >= -0.7 comparison.
+template <int MAXO>
+__device__ inline bool antsafe_notdone(const float (&nx)[MAXO], int O) {
+    bool fin = true;
+    for (int o = 0; o < O; ++o) fin = fin && isfinite(nx[o]);
+    float z = nx[0];
+    float q1 = nx[2], q2 = nx[3];
+    float zrot = __fsub_rn(1.0f, __fmul_rn(2.0f, __fadd_rn(__fmul_rn(q1, q1), __fmul_rn(q2, q2))));
+    bool flags = fin && (z >= 0.2f) && (z <= 1.0f);
+    float prod = __fmul_rn(flags ? 1.0f : 0.0f, zrot);   // False * nan = nan, as in numpy
+    return prod >= -0.7f;
+}
+
+template <int MAXO>
+__device__ inline void apply_statics(int term_id, int cost_id, const float (&nx)[MAXO], int O,
+                                     bool& term, float& cost) {
+    bool done = false;
+    if (term_id == CMBPO_TERM_ANTSAFE) done = !antsafe_notdone(nx, O);           // statics.py:17-31
+    term = done;
+    if (cost_id == CMBPO_COST_HCS) {                                              // statics.py:10-15
+        float xd = __fmul_rn(nx[O - 1], 10.0f);
+        cost = (fabsf(xd) < 2.0f) ? 1.0f : 0.0f;
+    } else if (cost_id == CMBPO_COST_ANTSAFE) {                                   // statics.py:33-53
+        bool d2 = !antsafe_notdone(nx, O);
+        float c = (d2 ? 1.0f : 0.0f) + ((fabsf(nx[O - 1]) > 3.2f) ? 1.0f : 0.0f);
+        cost = fminf(fmaxf(c, 0.0f), 1.0f);
+    } else {
+        cost = 0.0f;                                                              // fake_env.py:146
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FakeEnv.step for one row (fake_env.py:104-153) given the raw last-layer outputs of all E
+// members.  `raw(e, c)` returns column c of member e for this row (c < 2*D).
+// ------------------------------------------------------------------------------------------
+struct EnvRowCfg {
+    int O, D, E;                 // D = O + 1 (+1 if the model predicts the cost)
+    int term_id, cost_id, predicts_cost, deterministic, predicts_delta;
+    const float* sig_out;        // [D] max(sqrt(var),1e-2)   (pens/utils.py:167)
+    const float* mu_out;         // [D]
+    const float* l2s_out;        // [D] 2*log(sigma)          (pens/utils.py:187)
+    const int* elite;            // [n_elite]
+};
+
+struct EnvRowOut {
+    float rew, cost, dkl_path, ep_var_mean, ep_var_sum;
+    bool term;
+};
+
+template <class Raw, int MAXO>
+__device__ inline EnvRowOut fakeenv_row(const EnvRowCfg& c, Raw raw, const float (&obs)[MAXO],
+                                        int elite_pos, const float* state_eps /*[O] or null*/,
+                                        float (&next_obs)[MAXO], float* ep_var_out /*[O] or null*/) {
+    const int O = c.O, E = c.E;
+    const int member = c.elite[elite_pos];
+    float kl[MAXO], epv[MAXO];
+    const float den = (float)((double)(E * (E - 1)) + 1e-10);   // pens/utils.py:56
+    for (int o = 0; o < O; ++o) {
+        float nd[CMBPO_MAX_E], ls[CMBPO_MAX_E], vr[CMBPO_MAX_E];
+        const float sg = c.sig_out[o], mu = c.mu_out[o], l2s = c.l2s_out[o];
+        float sel = 0.f;
+#pragma unroll
+        for (int e = 0; e < CMBPO_MAX_E; ++e) {
+            if (e < E) {
+                float mean = __fadd_rn(__fmul_rn(sg, raw(e, o)), mu);           // pe.py:815-821
+                float logvar = __fadd_rn(l2s, raw(e, c.D + o));                  // pe.py:826-828
+                float var = expf(logvar);                                        // pe.py:833
+                float sd = sqrtf(var);                                           // fake_env.py:104
+                float x = mean;
+                if (!c.deterministic) {                                          // fake_env.py:105-106
+                    float m = state_eps ? state_eps[o] : 1.0f;
+                    x = __fadd_rn(mean, __fmul_rn(sd, m));
+                }
+                nd[e] = x;
+                float l = logf(sd);                                              // pens/utils.py:46-47
+                l = fminf(fmaxf(l, -100.0f), 1e8f);
+                ls[e] = l;
+                vr[e] = expf(__fmul_rn(2.0f, l));                                // pens/utils.py:20
+                if (e == member) sel = x;
+            }
+        }
+        // np.var over the member axis (fake_env.py:112): sequential sums, true divides
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < CMBPO_MAX_E; ++e) if (e < E) s = (e == 0) ? nd[0] : __fadd_rn(s, nd[e]);
+        float m = __fdiv_rn(s, (float)E);
+        float q = 0.f;
+#pragma unroll
+        for (int e = 0; e < CMBPO_MAX_E; ++e) if (e < E) {
+            float d = __fsub_rn(nd[e], m);
+            float d2 = __fmul_rn(d, d);
+            q = (e == 0) ? d2 : __fadd_rn(q, d2);
+        }
+        epv[o] = __fdiv_rn(q, (float)E);
+        // average_dkl (pens/utils.py:30-57): all ordered pairs, i outer / j inner
+        float acc = 0.f;
+        bool first = true;
+#pragma unroll
+        for (int i = 0; i < CMBPO_MAX_E; ++i) {
+#pragma unroll
+            for (int j = 0; j < CMBPO_MAX_E; ++j) {
+                if (i < E && j < E) {
+                    float dm = __fsub_rn(nd[j], nd[i]);
+                    float num = __fadd_rn(__fmul_rn(dm, dm), vr[i]);
+                    float ratio = __fdiv_rn(num, __fadd_rn(vr[j], 1e-10f));
+                    float pre = __fsub_rn(__fadd_rn(__fmul_rn(0.5f, __fsub_rn(ratio, 1.0f)), ls[j]), ls[i]);
+                    // np.clip(pre, 0, 1e10): nan propagates
+                    float k = (pre != pre) ? pre : fminf(fmaxf(pre, 0.0f), 1e10f);
+                    acc = first ? k : __fadd_rn(acc, k);
+                    first = false;
+                }
+            }
+        }
+        kl[o] = __fdiv_rn(acc, den);
+        next_obs[o] = c.predicts_delta ? __fadd_rn(sel, obs[o]) : sel;               // fake_env.py:125-131
+        if (ep_var_out) ep_var_out[o] = epv[o];
+    }
+    EnvRowOut r;
+    r.dkl_path = __fdiv_rn(np_sum_f32(kl, O), (float)O);                         // fake_env.py:113
+    float es = np_sum_f32(epv, O);
+    r.ep_var_sum = es;
+    r.ep_var_mean = __fdiv_rn(es, (float)O);                                     // model_sampler.py:343
+    apply_statics(c.term_id, c.cost_id, next_obs, O, r.term, r.cost);            // fake_env.py:134-146
+    int rcol = c.D - 1;
+    if (c.predicts_cost) {                                                       // fake_env.py:139-142
+        r.cost = __fadd_rn(__fmul_rn(c.sig_out[rcol], raw(member, rcol)), c.mu_out[rcol]);
+        rcol -= 1;
+    }
+    r.rew = __fadd_rn(__fmul_rn(c.sig_out[rcol], raw(member, rcol)), c.mu_out[rcol]);  // :148-151
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gaussian actor head for one row (ac_network.py:105-111, 46-48)
+// ------------------------------------------------------------------------------------------
+template <int MAXA>
+__device__ inline float actor_row(const float (&mu)[MAXA], const float* log_std, const float (&eps)[MAXA],
+                                  int A, float (&pi)[MAXA]) {
+    float terms[MAXA];
+    const float log2pi = 1.8378770664093453f;   // float32(np.log(2*np.pi))
+    for (int a = 0; a < A; ++a) {
+        float ls = log_std[a];
+        float sd = expf(ls);
+        pi[a] = __fadd_rn(mu[a], __fmul_rn(eps[a], sd));                         // ac_network.py:109
+        float z = __fdiv_rn(__fsub_rn(pi[a], mu[a]), __fadd_rn(sd, 1e-8f));
+        float t = __fadd_rn(__fadd_rn(__fmul_rn(z, z), __fmul_rn(2.0f, ls)), log2pi);
+        terms[a] = __fmul_rn(-0.5f, t);                                          // ac_network.py:47
+    }
+    return np_sum_f32(terms, A);
+}

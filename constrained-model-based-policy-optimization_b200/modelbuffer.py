@@ -1,0 +1,174 @@
+"""`ModelBuffer` with the reference's contract (buffers/modelbuffer.py:18-226), backed by
+time-major device buffers.  GAE / cost-GAE run in cmbpo_gae_paths, the advantage statistics,
+normalisation and the populated-mask flatten of get() in cmbpo_adv_* / cmbpo_compact_field.
+"""
+import numpy as np
+
+from . import _lib as L
+from .rollout import RolloutBuffers
+
+EPS = 1e-8
+
+
+class ModelBuffer:
+    def __init__(self, batch_size, obs_dim, act_dim, max_path_length, engine=None, *args, **kwargs):
+        if engine is None:
+            raise L.CmbpoError("ModelBuffer needs the Engine that owns the device buffers")
+        self.engine = engine
+        self.max_path_length = int(max_path_length)
+        self.batch_size = int(batch_size)
+        self.obs_shape, self.act_shape = obs_dim, act_dim
+        self.obs_dim = int(np.prod(obs_dim))
+        self.act_dim = int(np.prod(act_dim))
+        self.pi_info_shapes = None
+        self.gamma, self.lam, self.cost_gamma, self.cost_lam = 0.99, 0.95, 0.99, 0.95
+        self.reduce_fn = None        # set by the multi-GPU wrapper: all-reduce of the statistics
+        self.scan_mode = L.SCAN_STRICT
+        self.reset()
+
+    def initialize(self, pi_info_shapes, gamma=0.99, lam=0.95, cost_gamma=0.99, cost_lam=0.95):
+        """modelbuffer.py:41-51."""
+        self.pi_info_shapes = dict(pi_info_shapes)
+        self.sorted_pi_info_keys = sorted(self.pi_info_shapes)
+        assert self.sorted_pi_info_keys == ["log_std", "mu"], "Gaussian policy pi_info expected"
+        self.gamma, self.lam = gamma, lam
+        self.cost_gamma, self.cost_lam = cost_gamma, cost_lam
+
+    def reset(self, batch_size=None):
+        """modelbuffer.py:53-98: fresh zeroed buffers sized to the batch."""
+        if batch_size is not None:
+            self.batch_size = int(batch_size)
+        self.bufs = RolloutBuffers(self.engine, self.batch_size, self.max_path_length,
+                                   self.obs_dim, self.act_dim)
+        self.ptr, self.path_start_idx = 0, 0
+        self.max_size = np.ones(self.batch_size) * self.max_path_length
+        self.terminated_paths_mask = np.zeros(self.batch_size, dtype=bool)
+        self._length = np.zeros(self.batch_size, dtype=np.int32)   # host mirror (step-wise mode)
+        self._last_val = np.zeros(self.batch_size, dtype=np.float32)
+        self._last_cval = np.zeros(self.batch_size, dtype=np.float32)
+        self._device_lengths = False     # True once a fused rollout owns length/last_val on device
+        self._log_std_row = None
+
+    # ---- properties of the reference -------------------------------------------------------
+    @property
+    def populated_mask(self):
+        if self._device_lengths:
+            return self.bufs.populated_mask()
+        return np.arange(self.max_path_length)[None, :] < self._length[:, None]
+
+    @property
+    def size(self):
+        return int(self.populated_mask.sum())
+
+    @property
+    def has_room(self):
+        return bool((self.ptr < self.max_size).all())
+
+    @property
+    def alive_paths(self):
+        return np.logical_not(self.terminated_paths_mask)
+
+    def __getattr__(self, name):
+        # reference attribute names, e.g. obs_buf / adv_buf / term_buf, as [B, T, ...] numpy copies
+        table = {"obs_buf": "obs", "act_buf": "act", "nextobs_buf": "nextobs", "rew_buf": "rew",
+                 "val_buf": "val", "cost_buf": "cost", "cval_buf": "cval", "logp_buf": "logp",
+                 "dyn_error_buf": "dyn_error", "adv_buf": "adv", "ret_buf": "ret",
+                 "cadv_buf": "cadv", "cret_buf": "cret", "term_buf": "term"}
+        if name in table and "bufs" in self.__dict__:
+            return self.bufs.host(table[name])
+        raise AttributeError(name)
+
+    # ---- step-wise interface (external policy) ------------------------------------------------
+    def store_multiple(self, obs, act, next_obs, rew, val, cost, cval, dyn_error, logp, pi_info, term):
+        """modelbuffer.py:114-135: row i of every argument goes to the i-th alive path, column ptr."""
+        assert (self.ptr < self.max_size).all()
+        e, t = self.engine, self.engine.torch
+        alive_idx = np.flatnonzero(self.alive_paths).astype(np.int32)
+        n = len(alive_idx)
+        idx = e.to_device(alive_idx, t.int32)
+        B, b = self.batch_size, self.bufs
+
+        def put(dst, src, width):
+            src = e.to_device(np.asarray(src, np.float32).reshape(n, width), t.float32)
+            e.scatter_rows(dst, B, width, self.ptr, idx, src)
+
+        put(b.obs, obs, self.obs_dim); put(b.act, act, self.act_dim)
+        put(b.nextobs, next_obs, self.obs_dim); put(b.mu, pi_info["mu"], self.act_dim)
+        for dst, src in ((b.rew, rew), (b.val, val), (b.cost, cost), (b.cval, cval),
+                         (b.logp, logp), (b.dyn_error, dyn_error)):
+            put(dst, src, 1)
+        tcol = b.term[self.ptr]
+        tcol[idx.long()] = e.to_device(np.asarray(term, bool).astype(np.uint8).reshape(n), t.uint8)
+        if n:
+            self._log_std_row = np.asarray(pi_info["log_std"], np.float32).reshape(n, -1)[0].copy()
+        self._length[alive_idx] = self.ptr + 1
+        self.ptr += 1
+
+    def finish_path_multiple(self, term_mask, last_val=0, last_cval=0):
+        """modelbuffer.py:138-182: GAE + cost-GAE for the paths being closed, at close time."""
+        term_mask = np.asarray(term_mask, dtype=bool)
+        if not term_mask.any():
+            return
+        assert self.alive_paths.sum() == len(term_mask)
+        alive_idx = np.flatnonzero(self.alive_paths)
+        fin = alive_idx[term_mask]
+        if self.ptr > 0:
+            e, t = self.engine, self.engine.torch
+            len_now = np.zeros(self.batch_size, np.int32)
+            len_now[fin] = self.ptr
+            lv = np.zeros(self.batch_size, np.float32)
+            lc = np.zeros(self.batch_size, np.float32)
+            lv[fin] = np.asarray(last_val, np.float32)
+            lc[fin] = np.asarray(last_cval, np.float32)
+            self._last_val[fin], self._last_cval[fin] = lv[fin], lc[fin]
+            b = self.bufs
+            e.gae_paths(b.rew, b.val, b.cost, b.cval, e.to_device(len_now, t.int32),
+                        e.to_device(lv), e.to_device(lc), self.gamma, self.lam, self.cost_gamma,
+                        self.cost_lam, self.batch_size, self.max_path_length, 1, self.batch_size,
+                        out=(b.adv, b.ret, b.cadv, b.cret), scan=self.scan_mode)
+        # a path closed before its first store contributes nothing (modelbuffer.py:160)
+        self.terminated_paths_mask[fin] = True
+
+    # ---- fused interface --------------------------------------------------------------------
+    def adopt_device_rollout(self, log_std_row):
+        """Called by ModelSampler after a fused rollout filled `self.bufs` on the device."""
+        self._device_lengths = True
+        self._log_std_row = np.asarray(log_std_row, np.float32)
+
+    def finish_all_device(self):
+        """GAE for every path from the device-resident (length, last_val, last_cval)."""
+        self.bufs.gae(self.gamma, self.lam, self.cost_gamma, self.cost_lam, scan=self.scan_mode)
+        self.terminated_paths_mask[:] = True
+
+    # ---- get ---------------------------------------------------------------------------------
+    def get_device(self):
+        """get() without the device->host copy: (list of 12 device tensors, diagnostics)."""
+        assert self.terminated_paths_mask.all()
+        e, t, b = self.engine, self.engine.torch, self.bufs
+        B, T = self.batch_size, self.max_path_length
+        if not self._device_lengths:
+            b.length.copy_(e.to_device(self._length, t.int32))
+        st = e.adv_statistics(b.adv, b.cadv, b.ret, b.cret, B, T, 1, B, b.length, self.reduce_fn)
+        if st["n"] > 0:
+            e.adv_normalise(b.adv, b.cadv, B, T, 1, B, b.length, st)
+        off = e.path_offsets(b.length)
+        n_rows = int(off[-1].item())
+        O, A = self.obs_dim, self.act_dim
+        out = [e.compact(b.obs, B, T, O, b.length, off, n_rows),
+               e.compact(b.act, B, T, A, b.length, off, n_rows)]
+        for f in (b.adv, b.cadv, b.ret, b.cret, b.logp, b.val, b.cval, b.cost):
+            out.append(e.compact(f, B, T, 1, b.length, off, n_rows))
+        mu = e.compact(b.mu, B, T, A, b.length, off, n_rows)
+        ls_row = self._log_std_row if self._log_std_row is not None else np.zeros(A, np.float32)
+        log_std = e.to_device(ls_row, t.float32).reshape(1, A).expand(n_rows, A).contiguous()
+        out += [log_std, mu]                       # sorted pi_info keys: log_std, mu
+        diag = dict(poolm_batch_size=n_rows, poolm_ret_mean=st["ret_mean"],
+                    poolm_cret_mean=st["cret_mean"])
+        return out, diag
+
+    def get(self):
+        """modelbuffer.py:184-226.  Returns numpy copies and resets, like the reference."""
+        out, diag = self.get_device()
+        res = [x.cpu().numpy() for x in out]
+        self.reset()
+        return res, diag

@@ -1,0 +1,248 @@
+/*
+ * cmbpo_b200.h -- C ABI of libcmbpo_b200.so: the B200 (sm_100a) implementation of CMBPO's
+ * model-rollout + GAE hot path.
+ *
+ * The reference (anyboby/Constrained-Model-Based-Policy-Optimization) has no FFI: its boundary
+ * is three duck-typed Python interfaces.  Every entry point below names the reference
+ * interface (file:line, relative to the reference root) whose arithmetic it replaces; the
+ * Python classes in constrained-model-based-policy-optimization_b200/ keep the reference's
+ * signatures and call these through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; cmbpo_last_error() returns
+ *     a thread-local message for the last failure;
+ *   - all tensor pointers are DEVICE pointers (on the context's device) unless the name
+ *     ends in _host; the caller owns them;
+ *   - work is enqueued on the context's stream (cmbpo_ctx_set_stream) with no host
+ *     synchronisation unless stated;
+ *   - float = IEEE binary32; masks are uint8 (0/1); indices int32.
+ *   - there is no CPU fallback: without a CUDA device cmbpo_ctx_create fails.
+ */
+#ifndef CMBPO_B200_H
+#define CMBPO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMBPO_ABI_VERSION 1
+
+typedef struct cmbpo_ctx cmbpo_ctx;
+
+/* which network a call addresses */
+enum { CMBPO_NET_DYN = 0,   /* dynamics PE: models/pens/pe.py, built at algorithms/cmbpo.py:120-136 */
+       CMBPO_NET_V = 1,     /* value ensemble:      policies/cpo_policy.py:467 */
+       CMBPO_NET_VC = 2,    /* cost-value ensemble: policies/cpo_policy.py:468 */
+       CMBPO_NET_ACTOR = 3, /* Gaussian actor mean MLP: network/ac_network.py:99-123 (E = 1) */
+       CMBPO_NET_COUNT = 4 };
+
+/* models/pens/fc.py:13-20 */
+enum { CMBPO_ACT_NONE = 0, CMBPO_ACT_SWISH = 1, CMBPO_ACT_TANH = 2, CMBPO_ACT_RELU = 3,
+       CMBPO_ACT_SIGMOID = 4 };
+
+/* arithmetic of the GEMM chain */
+enum { CMBPO_PREC_FP32 = 0,   /* CUDA-core fp32: the variant that isolates logic from precision */
+       CMBPO_PREC_BF16 = 1,   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
+       CMBPO_PREC_FP16 = 2 }; /* tcgen05 kind::f16, fp16 operands (tf32-class mantissa), fp32 accumulate */
+
+/* models/statics.py:56-70 */
+enum { CMBPO_TERM_NO_DONE = 0, CMBPO_TERM_ANTSAFE = 1 };
+enum { CMBPO_COST_ZERO = 0, CMBPO_COST_HCS = 1, CMBPO_COST_ANTSAFE = 2 };
+
+/* why a model path ended (samplers/model_sampler.py:275-367, 418-444) */
+enum { CMBPO_END_ALIVE = 0, CMBPO_END_UNCERTAIN = 1, CMBPO_END_HORIZON = 2, CMBPO_END_TERMINAL = 3,
+       CMBPO_END_CAPPED = 4,  /* max_samples cap, model_sampler.py:282-287 */
+       CMBPO_END_STOPPED = 5  /* finish_all_paths after the caller stopped, model_sampler.py:418-444 */ };
+
+/* GAE scan flavour */
+enum { CMBPO_SCAN_STRICT = 0, /* float64, strictly sequential: bit-identical to scipy.signal.lfilter */
+       CMBPO_SCAN_WARP = 1 }; /* float64 warp-shuffle segmented scan (re-associated; <= 1 ulp after the fp32 round) */
+
+int cmbpo_abi_version(void);
+const char* cmbpo_last_error(void);
+
+int cmbpo_ctx_create(int device, cmbpo_ctx** out);
+int cmbpo_ctx_destroy(cmbpo_ctx* ctx);
+int cmbpo_ctx_set_stream(cmbpo_ctx* ctx, void* cuda_stream);
+int cmbpo_ctx_synchronize(cmbpo_ctx* ctx);
+/* number of this library's kernels launched on the context since creation (bench.py's gpu_launches) */
+int64_t cmbpo_ctx_launch_count(cmbpo_ctx* ctx);
+
+/*
+ * Upload one network.  Replaces the TF variables behind models/pens/fc.py:123-170 (weights
+ * [E,in,out], biases [E,1,out]) and models/pens/utils.py:104-111 (scaler mu/var [1,dim]).
+ *   dims[n_layers+1], W[l] -> [E, dims[l], dims[l+1]], b[l] -> [E, dims[l+1]], acts[n_layers].
+ *   For a probabilistic net dims[n_layers] = 2*D (mean | logvar), models/pens/pe.py:179-180.
+ *   mu_* / var_* may be NULL (no scaler).  elite_inds: models/pens/pe.py:396-403 (may hold duplicates).
+ *   on_device != 0: the arrays are already on the device (e.g. after an NCCL broadcast).
+ */
+int cmbpo_net_set_weights(cmbpo_ctx* ctx, int which, int E, int n_layers, const int* dims_host,
+                          const float* const* W, const float* const* b, const int* acts_host,
+                          const float* mu_in, const float* var_in, const float* mu_out,
+                          const float* var_out, int probabilistic, const int* elite_inds_host,
+                          int n_elite, int on_device);
+/* state-independent log_std of the actor, network/ac_network.py:104 */
+int cmbpo_actor_set_log_std(cmbpo_ctx* ctx, const float* log_std, int A, int on_device);
+
+/*
+ * PE.predict_ensemble (models/pens/pe.py:671-713 -> _compile_outputs 789-838).
+ *   x: [N, in] (x_is_3d = 0, fc.py:87-88) or [E, N, in] (x_is_3d = 1, fc.py:89-90).
+ *   mean, var: [E, N, D]; var may be NULL for a non-probabilistic net.
+ */
+int cmbpo_ens_predict(cmbpo_ctx* ctx, int which, const float* x, int64_t N, int x_is_3d,
+                      float* mean, float* var, int precision);
+/* PE.predict (pe.py:648-669, tensors 326-330 / 343): mean over ALL members -> [N, D]; var may be NULL */
+int cmbpo_ens_predict_mean(cmbpo_ctx* ctx, int which, const float* x, int64_t N, float* mean,
+                           float* var, int precision);
+
+/*
+ * CPOPolicy.get_action_outs (policies/cpo_policy.py:801-823; ac_network.py:99-123, 46-48).
+ *   eps: [N, A] injected standard normals, or NULL -> Philox4x32-10 keyed (seed, path id, step).
+ *   path_ids: [N] global path id per row (NULL -> row index).  Outputs: pi, mu [N,A]; logp, v, vc [N].
+ */
+int cmbpo_policy_act(cmbpo_ctx* ctx, const float* obs, int64_t N, const float* eps,
+                     const int32_t* path_ids, uint64_t seed, int step, float* pi, float* logp,
+                     float* mu, float* v, float* vc, int precision);
+
+/*
+ * FakeEnv.step for 2-D inputs (models/fake_env.py:66-172) with an ensemble, probabilistic,
+ * delta-predicting model that also predicts the reward (algorithms/cmbpo.py:137-142).
+ *   elite_pos: [N] positions into elite_inds (what np.random.choice draws, fake_env.py:174-176)
+ *              or NULL -> Philox.   state_eps: [N,O] multiplier of std when deterministic = 0
+ *              (NULL -> 1, the reference's `+ std`, fake_env.py:105-106).
+ *   next_obs [N,O], rew [N], cost [N], term [N] u8, dkl_path [N], ep_var [N,O],
+ *   dkl_mean_out: 1 float (ensemble_dkl_mean).
+ */
+typedef struct {
+    int term_id, cost_id;      /* models/statics.py tables */
+    int predicts_cost;         /* fake_env.py:139-142 */
+    int deterministic;         /* fake_env.py:105-108 */
+    int predicts_delta;        /* fake_env.py:130-131 */
+} cmbpo_env_cfg;
+
+int cmbpo_fakeenv_step(cmbpo_ctx* ctx, const cmbpo_env_cfg* cfg, const float* obs, const float* act,
+                       int64_t N, const int32_t* elite_pos, const float* state_eps,
+                       const int32_t* path_ids, uint64_t seed, int step, float* next_obs, float* rew,
+                       float* cost, uint8_t* term, float* dkl_path, float* ep_var,
+                       float* dkl_mean_out, int precision);
+
+/*
+ * The H-step model rollout: ModelSampler.reset + sample x (T-1) (samplers/model_sampler.py:203-375)
+ * writing what ModelBuffer.store_multiple would (buffers/modelbuffer.py:114-135), for B start
+ * states.  Per-path rules (uncertainty cut-off, horizon, env terminal) are applied in the
+ * kernel; the two batch-global rules (max_samples cap, alive-ratio stop) are a truncation
+ * applied afterwards by cmbpo_rollout_truncate.
+ *
+ * Buffers are TIME-MAJOR: field[t][p][...] with t < T = max_path_length, p < B, so that one
+ * step of 128 consecutive paths is one contiguous, coalesced block.
+ */
+typedef struct {
+    /* inputs */
+    const float* start_obs;      /* [B,O] */
+    const float* act_eps;        /* [T,B,A] or NULL (Philox) */
+    const int32_t* elite_pos;    /* [T,B]   or NULL (Philox) */
+    const float* state_eps;      /* [T,B,O] or NULL */
+    /* per-step fields, time-major */
+    float *obs, *act, *nextobs, *mu;               /* [T,B,O], [T,B,A], [T,B,O], [T,B,A] */
+    float *rew, *val, *cost, *cval, *logp, *dyn_error, *dkl; /* [T,B] */
+    uint8_t* term;                                 /* [T,B] */
+    /* per-path results */
+    int32_t* length;             /* [B] stored steps */
+    uint8_t* end_reason;         /* [B] CMBPO_END_* */
+    float *last_val, *last_cval; /* [B] bootstrap values for the GAE pass */
+    double *cum_dkl, *path_return, *path_cost; /* [B] float64 accumulators, model_sampler.py:218-226 */
+    float* final_obs;            /* [B,O] observation each path stopped at */
+    double* step_stats;          /* [T,4] per step: rows fed to the model, sum of dkl_path over them,
+                                    rows stored, sum of ensemble_ep_var over the stored rows */
+} cmbpo_rollout_bufs;
+
+typedef struct {
+    int64_t B;                   /* start states on this rank */
+    int64_t path_id_base;        /* global id of path 0 (multi-GPU shard offset; keys the Philox streams) */
+    int T;                       /* max_path_length (maxroll); at most T-1 steps are stored, model_sampler.py:352 */
+    int max_steps;               /* stop after this many steps (<= T-1), <=0 -> T-1 */
+    int uncertainty_mode;        /* rollout_mode == 'uncertainty', model_sampler.py:275 */
+    double dkl_lim;              /* model_sampler.py:171-172 */
+    uint64_t seed;
+    int precision;
+    cmbpo_env_cfg env;
+} cmbpo_rollout_cfg;
+
+int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const cmbpo_rollout_bufs* bufs);
+
+/*
+ * Batch-global rules of the sampler, applied to a finished speculative rollout as a truncation
+ * (paths are independent, so cutting path p at step t only shortens it):
+ *   - max_samples cap (model_sampler.py:282-287): at step cap_step the first cap_n surviving paths
+ *     BY PATH INDEX are closed before the step is stored, bootstrapped with V(s_t), VC(s_t);
+ *   - stop (algorithms/cmbpo.py:258-263 then model_sampler.py:418-444 finish_all_paths): after step
+ *     stop_step every path still alive is closed, bootstrapped with V(s_{t+1}), VC(s_{t+1}).
+ * The host decides cap_step / cap_n / stop_step from the histogram (host-synchronous, 2*(T+1)
+ * int64: count(length == L) and count(length == L and end_reason == UNCERTAIN)).
+ * Pass cap_step < 0 / stop_step < 0 to skip a rule.
+ */
+int cmbpo_rollout_histogram(cmbpo_ctx* ctx, const int32_t* length, const uint8_t* end_reason,
+                            int64_t B, int T, int64_t* hist_host);
+int cmbpo_rollout_truncate(cmbpo_ctx* ctx, const cmbpo_rollout_bufs* bufs, int64_t B, int T,
+                           int cap_step, int64_t cap_n, int stop_step);
+
+/*
+ * GAE + cost-GAE + returns over finished paths
+ * (buffers/modelbuffer.py:163-179, buffers/cpobuffer.py:179-207, utilities/utils.py:159-211).
+ *   element (p, t) of every field lives at p*path_stride + t*time_stride (in floats).
+ *   length[p] steps are valid; last_val/last_cval [n_paths].  Writes adv, ret, cadv, cret for
+ *   t < length[p] only.
+ */
+int cmbpo_gae_paths(cmbpo_ctx* ctx, const float* rew, const float* val, const float* cost,
+                    const float* cval, int64_t n_paths, int max_len, int64_t path_stride,
+                    int64_t time_stride, const int32_t* length, const float* last_val,
+                    const float* last_cval, double gamma, double lam, double cgamma, double clam,
+                    float* adv, float* ret, float* cadv, float* cret, int scan_mode);
+/* flat CPOBuffer layout: segment i = [seg_offsets[i], seg_offsets[i+1]) (cpobuffer.py:180, 206) */
+int cmbpo_gae_flat(cmbpo_ctx* ctx, const float* rew, const float* val, const float* cost,
+                   const float* cval, int64_t n, const int64_t* seg_offsets, int64_t n_seg,
+                   const float* last_val, const float* last_cval, double gamma, double lam,
+                   double cgamma, double clam, float* adv, float* ret, float* cadv, float* cret,
+                   int scan_mode);
+
+/*
+ * mpi_statistics_scalar (utilities/mpi_tools.py:71-92) pass 1 and 2 over the valid entries
+ * (valid = t < length[p] for the path layout; all n for the flat layout when length == NULL).
+ *   sums_out (device, 8 doubles): {n, sum_adv, sum_cadv, sum_ret, sum_cret, sumsq_adv(after pass 2), 0, 0}.
+ *   Multi-GPU: the caller all-reduces sums_out[0..4] between pass 1 and pass 2 and sums_out[5]
+ *   after pass 2 (the two Allreduce calls of mpi_tools.py:82-86).
+ */
+int cmbpo_adv_stats_pass1(cmbpo_ctx* ctx, const float* adv, const float* cadv, const float* ret,
+                          const float* cret, int64_t n_paths, int max_len, int64_t path_stride,
+                          int64_t time_stride, const int32_t* length, double* sums_out);
+int cmbpo_adv_stats_pass2(cmbpo_ctx* ctx, const float* adv, int64_t n_paths, int max_len,
+                          int64_t path_stride, int64_t time_stride, const int32_t* length,
+                          float adv_mean, double* sums_out);
+/* adv <- (adv-mean)/(std+1e-8), cadv <- cadv-cmean on valid entries (modelbuffer.py:198-204) */
+int cmbpo_adv_normalise(cmbpo_ctx* ctx, float* adv, float* cadv, int64_t n_paths, int max_len,
+                        int64_t path_stride, int64_t time_stride, const int32_t* length,
+                        float adv_mean, float adv_std, float cadv_mean);
+
+/*
+ * ModelBuffer.get()'s `buf[populated_mask]` (modelbuffer.py:218): gathers the valid (p,t)
+ * entries of a time-major field [T,B,width] into out[row,width], rows ordered path-major then
+ * time (numpy boolean-mask order).  row_offsets [B+1] = exclusive prefix sum of length
+ * (cmbpo_path_offsets).
+ */
+int cmbpo_path_offsets(cmbpo_ctx* ctx, const int32_t* length, int64_t B, int64_t* row_offsets);
+int cmbpo_compact_field(cmbpo_ctx* ctx, const float* field, int64_t B, int T, int width,
+                        const int32_t* length, const int64_t* row_offsets, float* out);
+
+/*
+ * ModelBuffer.store_multiple (modelbuffer.py:114-135) for callers that step an external policy:
+ * dst is a time-major field [T,B,width]; row i of src [n,width] goes to path path_idx[i], column t.
+ */
+int cmbpo_scatter_rows(cmbpo_ctx* ctx, float* dst, int64_t B, int width, int t,
+                       const int32_t* path_idx, const float* src, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMBPO_B200_H */
