@@ -93,9 +93,15 @@ def test_statics_truth_table(engine):
     act = np.zeros((len(obs), A), np.float32)
     env = cb.FakeEnv(ShapeEnv(O, A), task, model, True, True, False)
     nxt, r, term, info = env.step(obs, act, elite_pos=np.zeros(len(obs), int))
-    assert np.array_equal(nxt, obs, equal_nan=True)
-    assert np.array_equal(term, orc.antsafe_term(obs))
-    assert np.array_equal(info["cost"], orc.antsafe_cost(obs))
+    # a NaN/inf anywhere in the input row poisons the whole prediction (0 * nan), in the reference too
+    oenv = orc.OracleFakeEnv(O, A, task, orc.OracleModel(dyn), lambda e, n: np.zeros(n, int))
+    wn, _, wt, winfo = oenv.step(obs, act)
+    clean = np.isfinite(obs).all(1)
+    assert np.array_equal(nxt[clean], obs[clean]) and np.array_equal(np.isnan(nxt), np.isnan(wn))
+    assert np.array_equal(term, wt) and np.array_equal(info["cost"], winfo["cost"])
+    assert np.array_equal(term, orc.antsafe_term(nxt))
+    assert np.array_equal(info["cost"], orc.antsafe_cost(nxt))
+    assert term[clean].any() and not term[clean].all()
     # HCS cost threshold |10 x| < 2
     task, O, A = TASKS["hcs"]
     dyn, actor, v, vc = orc.make_problem(32, O, A, hidden=(64, 64), task=task)

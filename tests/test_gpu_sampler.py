@@ -32,10 +32,6 @@ def _oracle_cycle(dyn, actor, v, vc, task, obs, noise, T, mode, lim, max_samples
     smp.initialize(env, policy, pool)
     smp.set_rollout_dkl(lim)
     smp.reset(obs)
-    smp._total_samples = 0
-
-    class _S:      # adapt attribute names
-        pass
     while True:
         _, _, _, info = smp.sample(max_samples)
         if max_samples and smp.total_samples >= 0.99 * max_samples:

