@@ -89,6 +89,29 @@ extern "C" int cmbpo_ctx_synchronize(cmbpo_ctx* ctx) {
 
 extern "C" int64_t cmbpo_ctx_launch_count(cmbpo_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int cmbpo_ctx_profile(cmbpo_ctx* ctx, int enable) {
+    CMBPO_CHECK(ctx, "null context");
+    ctx->profile = enable != 0;
+    return 0;
+}
+
+extern "C" int cmbpo_ctx_profile_read(cmbpo_ctx* ctx, int slot, double* total_ms, int64_t* launches,
+                                      int reset) {
+    CMBPO_CHECK(ctx && slot >= 0 && slot < CMBPO_PROF_SLOTS, "bad arguments");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ProfSlot& p = ctx->prof[slot];
+    double ms = 0;
+    for (size_t i = 0; i < p.used; ++i) {
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, p.start[i], p.stop[i]));
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (int64_t)p.used;
+    if (reset) p.used = 0;
+    return 0;
+}
+
 // sigma = max(sqrt(var), 1e-2) (pens/utils.py:156); l2s = 2*log(sigma) (pens/utils.py:187)
 __global__ void prep_scaler_kernel(const float* var, int n, float* sig, float* l2s) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

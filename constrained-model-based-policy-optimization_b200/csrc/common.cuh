@@ -60,7 +60,14 @@ struct Workspace {
     size_t bytes = 0;
 };
 
+struct ProfSlot {
+    std::vector<cudaEvent_t> start, stop;
+    size_t used = 0;
+};
+
 struct cmbpo_ctx {
+    bool profile = false;
+    ProfSlot prof[CMBPO_PROF_SLOTS];
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
@@ -73,6 +80,27 @@ struct cmbpo_ctx {
 
 // grow-only scratch
 int cmbpo_ws_get(cmbpo_ctx* ctx, int slot, size_t bytes, void** out);
+
+// RAII bracket: records start/stop events around a launch when profiling is on
+struct ProfScope {
+    cmbpo_ctx* ctx; int slot; bool on;
+    ProfScope(cmbpo_ctx* c, int s) : ctx(c), slot(s), on(c->profile && s >= 0) {
+        if (!on) return;
+        ProfSlot& p = ctx->prof[slot];
+        if (p.used == p.start.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            p.start.push_back(a); p.stop.push_back(b);
+        }
+        cudaEventRecord(p.start[p.used], ctx->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        ProfSlot& p = ctx->prof[slot];
+        cudaEventRecord(p.stop[p.used], ctx->stream);
+        p.used++;
+    }
+};
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -198,6 +198,7 @@ int ens_forward_f32(cmbpo_ctx* ctx, const Net& net, const float* x, int64_t N, b
 
 int ens_forward(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, bool x_is_3d, float* out_raw,
                 int precision) {
+    ProfScope prof(ctx, (&net == &ctx->nets[CMBPO_NET_DYN]) ? CMBPO_PROF_DYN : -1);
     if (precision == CMBPO_PREC_FP32) return ens_forward_f32(ctx, net, x, N, x_is_3d, out_raw);
     CMBPO_CHECK(!x_is_3d, "tcgen05 path takes 2-D inputs only");
     CMBPO_CHECK(ens_tc_supported(net),

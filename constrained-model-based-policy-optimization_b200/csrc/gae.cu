@@ -397,6 +397,7 @@ extern "C" int cmbpo_gae_paths(cmbpo_ctx* ctx, const float* rew, const float* va
     CMBPO_CHECK(ctx, "null context");
     if (n_paths <= 0 || max_len <= 0) return 0;
     GaeK k = make_k(gamma, lam, cgamma, clam);
+    ProfScope prof(ctx, CMBPO_PROF_GAE);
     if (scan_mode == CMBPO_SCAN_WARP) {
         int threads = 256;
         int64_t blocks = (n_paths * 32 + threads - 1) / threads;
@@ -437,6 +438,7 @@ extern "C" int cmbpo_gae_flat(cmbpo_ctx* ctx, const float* rew, const float* val
     (void)n;
     if (n_seg <= 0) return 0;
     GaeK k = make_k(gamma, lam, cgamma, clam);
+    ProfScope prof(ctx, CMBPO_PROF_GAE);
     int threads = 256;
     if (scan_mode == CMBPO_SCAN_WARP) {
         int64_t blocks = (n_seg * 32 + threads - 1) / threads;

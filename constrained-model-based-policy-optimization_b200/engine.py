@@ -81,6 +81,16 @@ class Engine:
     def launch_count(self):
         return int(self.lib.cmbpo_ctx_launch_count(self.h))
 
+    def profile(self, enable=True):
+        """Bracket the dominant kernels (dynamics GEMM chain, GAE scan) with CUDA events."""
+        L.check(self.lib.cmbpo_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self, slot, reset=True):
+        """(summed device ms, launches) of slot 0 = dynamics GEMM chain, 1 = GAE scan."""
+        ms, n = C.c_double(), C.c_int64()
+        L.check(self.lib.cmbpo_ctx_profile_read(self.h, slot, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
+
     # ------------------------------------------------------------------ weights
     def set_network(self, which, W, b, acts, mu_in=None, var_in=None, mu_out=None, var_out=None,
                     probabilistic=False, elite_inds=()):

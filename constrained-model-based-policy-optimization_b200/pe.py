@@ -32,6 +32,18 @@ class B200PE:
         return cls(engine, which, ens.W, ens.b, ens.acts, ens.probabilistic, ens.elite_inds,
                    ens.mu_in, ens.var_in, ens.mu_out, ens.var_out, name=name)
 
+    @classmethod
+    def view(cls, engine, which, name="PE"):
+        """A model object over a slot whose weights were already uploaded (Engine.set_network)."""
+        meta = engine.nets[which]
+        self = cls.__new__(cls)
+        self.engine, self.which, self.name = engine, which, name
+        self._probabilistic = meta["probabilistic"]
+        self.num_nets, self._in_dim, self._d = meta["E"], meta["dims"][0], meta["D"]
+        self._model_inds = list(meta["elite_inds"])
+        self.num_elites = len(self._model_inds)
+        return self
+
     # --- contract properties (pe.py:401-434) ---
     @property
     def elite_inds(self):

@@ -28,6 +28,13 @@ class B200Policy:
         self.log_std = np.asarray(log_std, np.float32).copy()
         self.act_dim = int(self.log_std.shape[0])
 
+    def attach_loaded(self, log_std):
+        """Use networks that were already uploaded to the engine (e.g. after an NCCL broadcast)."""
+        self.log_std = np.asarray(log_std, np.float32).copy()
+        self.act_dim = int(self.log_std.shape[0])
+        self.v = B200PE.view(self.engine, L.NET_V, name="VEnsemble")
+        self.vc = B200PE.view(self.engine, L.NET_VC, name="VCEnsemble")
+
     def load_values(self, v_ens, vc_ens):
         self.v = B200PE.from_oracle_ensemble(self.engine, L.NET_V, v_ens, name="VEnsemble")
         self.vc = B200PE.from_oracle_ensemble(self.engine, L.NET_VC, vc_ens, name="VCEnsemble")

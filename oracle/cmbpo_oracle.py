@@ -708,6 +708,7 @@ def make_scalers(rng, task, obs_dim, act_dim):
     mu = rng.standard_normal(O) * s
     flat = rng.choice(np.arange(5, O - 1), size=2, replace=False)
     s[flat] = 1e-3
+    mu[flat] = 0.5 * rng.standard_normal(2)
     if task == "AntSafe-v2":
         mu[0], s[0] = 0.6, 0.12                   # torso height, healthy in [0.2, 1.0]
         mu[1:5], s[1:5] = (0.8, 0.2, 0.2, 0.1), (0.1, 0.45, 0.45, 0.1)
@@ -751,7 +752,7 @@ def make_problem(seed, obs_dim, act_dim, hidden=(512, 512), num_nets=7, num_elit
                         True, scalers=dyn_sc, gain=gain)
     actor = make_actor(rng, obs_dim, act_dim, a_hidden)
     if data_scalers:      # the actor sees raw observations: fold (obs-mu)/sigma into layer 0
-        sig = np.sqrt(var_o)
+        sig = np.maximum(np.sqrt(var_o), 0.1)     # the actor has no scaler: keep its gains moderate
         w0 = actor.W[0].astype(np.float64)
         actor.W[0] = (w0 / sig[:, None]).astype(F32)
         actor.b[0] = (-(mu_o / sig) @ w0).astype(F32)
