@@ -257,6 +257,8 @@ def run_cuda(args, rank, world, local_rank):
     launches = eng.launch_count - launches0
     dyn_ms, dyn_n = eng.profile_read(L_PROF_DYN, True)
     gae_ms, gae_n = eng.profile_read(L_PROF_GAE, True)
+    step_ms, step_n = eng.profile_read(2, True)
+    pol_ms, pol_n = eng.profile_read(3, True)
     eng.profile(False)
 
     # ---- end to end through the public API: host start states in, host sample list out ----
@@ -354,6 +356,9 @@ def run_cuda(args, rank, world, local_rank):
             "e2e": {"value": e2e_n / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(obs_host.nbytes), "d2h_bytes_per_step": int(d2h),
                     "api": "ModelSampler.reset/sample/finish_all_paths + ModelBuffer.get (numpy in, numpy out)"},
+            "breakdown_ms_per_step": {"dynamics_gemm_chain": dyn_ms / args.steps, "policy_pass": pol_ms / args.steps,
+                                      "row_kernel": step_ms / args.steps, "gae": gae_ms / args.steps,
+                                      "note": "rank 0, CUDA events around each launch"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

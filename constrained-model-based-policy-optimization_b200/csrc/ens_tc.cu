@@ -1,30 +1,38 @@
 // K1 on the tensor cores: the 3-layer ensemble MLP chain  X -> act(X W0+b0) -> act(. W1+b1) -> . W2+b2
-// for one 128-row tile per CTA and all E members, with tcgen05.mma (kind::f16, fp32 accumulators
-// in TMEM), weights streamed from L2 by the bulk-copy engine as pre-swizzled shared-memory tile
-// images, and the hidden activations never leaving the SM:
+// for one 128-row tile per CTA and all E members, with tcgen05.mma (kind::f16, fp32 accumulators in
+// TMEM).  Hidden activations never leave the SM and never touch shared memory: they live in TENSOR
+// MEMORY as the A operand of the next layer (tcgen05.mma with A from TMEM), which leaves almost all
+// of shared memory to a 24-deep ring of weight tiles streamed from L2 by the bulk-copy engine
+// (pre-swizzled tile images, plain 1-D cp.async.bulk, no tensor maps).
 //
-//   layer 0   D[128 x 128-col chunk] = XA  x W0 chunk          (K = in_dim padded to 16)
-//             epilogue: bias + act -> 16-bit -> H1 panels in shared memory (A operand of layer 1)
-//   layer 1   D chunk = sum over 64-wide K panels  H1[kp] x W1[kp, chunk]
-//             epilogue: bias + act -> 16-bit -> one of two H2 half-chunk panels
-//   layer 2   OUT[128 x NP] += H2 half x W2[half rows, :]        (accumulated across chunks in TMEM)
-//             epilogue: + b2 -> raw outputs (fp32) to global
+//   TMEM columns (512):   H1  [0, HD/2)      layer-0 output, 16-bit packed 2/column  (A of layer 1)
+//                         D   2 x 64         fp32 accumulator chunks (double buffered)
+//                         H2  1-2 x 32       layer-1 output chunk, 16-bit packed       (A of layer 2)
+//                         OUT NP             layer-2 accumulator (all chunks accumulate into it)
+//   layer 0   D chunk[128 x 64] = XA(smem) x W0 chunk           (K = in_dim padded to 16)
+//             epilogue: +bias, act -> 16-bit -> tcgen05.st into H1
+//   layer 1   D chunk = sum over 64-wide K panels  H1[kp](tmem) x W1[kp, chunk]
+//             epilogue: +bias, act -> 16-bit -> tcgen05.st into an H2 buffer
+//   layer 2   OUT[128 x NP] += H2(tmem) x W2[chunk rows, :]
+//             epilogue: +b2 -> raw outputs (fp32) to global
 //
-// Warp roles (384 threads): warp 0 = weight producer (one lane), warp 1 = MMA issuer (one lane),
-// warp 2 = TMEM allocator, warps 4-11 = two epilogue warpgroups (each owns 64 of a chunk's 128 columns;
-// thread <-> row, TMEM lane = row).
+// Warp roles (384 threads): warp 0 = weight producer, warp 1 = MMA issuer (both run warp-uniform
+// loops; one lane issues), warp 2 = TMEM allocator, warps 4-11 = two epilogue warpgroups (thread <->
+// row <-> TMEM lane; each warpgroup owns 32 of a chunk's 64 columns).
 //
-// Replaces models/pens/fc.py:74-95 x3 + the input scaler of models/pens/utils.py:156 (fused into
-// the XA load).  The output scaler / exp are applied by the consumer (ens_head_kernel or the
-// rollout row math) exactly as on the fp32 path.
+// Replaces models/pens/fc.py:74-95 x3 + the input scaler of models/pens/utils.py:156 (fused into the
+// XA load).  The output scaler / exp are applied by the consumer (ens_head_kernel or the rollout row
+// math) exactly as on the fp32 path.
 #include "tc_common.cuh"
 
 using namespace tc;
 
 namespace {
 
-constexpr int PANEL = 16384;      // [128 rows x 64 el x 2 B]
 constexpr int NTHREADS = 384;
+constexpr int STAGE = 8192;       // [64 neurons x 64 k x 2 B] weight tile
+constexpr int NS = 24;            // ring depth: 192 KB in flight
+constexpr int XA_BYTES = 16384;   // [128 rows x 64 k x 2 B]
 
 struct Stage {        // one weight tile image in the packed stream
     int layer, n0, k0, rows;
@@ -34,30 +42,31 @@ struct Stage {        // one weight tile image in the packed stream
 struct TcParams {
     const uint8_t* wpack; unsigned long long member_bytes;
     const float* bias; int bias_stride;
-    int E, K0, KS0, Nout, NP;
+    int E, K0, KS0, Nout, NP, parts;             // parts = 2 when NP > 64 (layer-2 N split in halves)
     const float* x; long long N; int ldx;
     const float *mu_in, *sig_in;
     float* out; long long out_member_stride;   // out[e*stride + row*Nout + c]
     int ntiles;
+    unsigned long long* dbg;   // optional [grid][16] cycle counters (protocol timing aid)
 };
 
-__host__ __device__ constexpr int n_stages_of(int hd) { return hd == 512 ? 3 : 4; }
+// barrier indices
+enum { W_FULL = 0, W_EMPTY = NS, D_FULL = 2 * NS, D_EMPTY = 2 * NS + 2, H1_FULL = 2 * NS + 4,
+       H2_FULL = 2 * NS + 5, H2_EMPTY = 2 * NS + 7, OUT_FULL = 2 * NS + 9, OUT_EMPTY = 2 * NS + 10,
+       X_FULL = 2 * NS + 11, NBAR = 2 * NS + 12 };
+constexpr int SMEM_BAR = XA_BYTES + NS * STAGE;
+constexpr int SMEM_TOTAL = SMEM_BAR + NBAR * 8 + 16;
 
-template <int HD>
-struct Smem {
-    static constexpr int NC = HD / 128, KP = HD / 64, NS = n_stages_of(HD);
-    static constexpr int XA = 0;
-    static constexpr int H1 = XA + PANEL;
-    static constexpr int H2 = H1 + KP * PANEL;
-    static constexpr int WR = H2 + 2 * PANEL;
-    static constexpr int BAR = WR + NS * PANEL;
-    static constexpr int TOTAL = BAR + 512;
-    // barrier indices
-    static constexpr int W_FULL = 0, W_EMPTY = NS, D_FULL = 2 * NS, D_EMPTY = 2 * NS + 2,
-                         H1_FULL = 2 * NS + 4, H2_FULL = 2 * NS + 5, H2_EMPTY = 2 * NS + 7,
-                         OUT_FULL = 2 * NS + 9, OUT_EMPTY = 2 * NS + 10, X_FULL = 2 * NS + 11,
-                         NBAR = 2 * NS + 12;
-};
+template <bool DBG>
+__device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc) {
+    if (DBG) {
+        long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += (unsigned long long)(clock64() - t0);
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
 
 template <int ACT> __device__ __forceinline__ float activate(float x) {
     if (ACT == CMBPO_ACT_SWISH) return swish_fast(x);
@@ -65,159 +74,194 @@ template <int ACT> __device__ __forceinline__ float activate(float x) {
     return x;
 }
 
-// 64 accumulator columns of this thread's row -> bias + act -> 16-bit -> 8 swizzled 16-B chunks
+// 32 accumulator columns of this thread's row -> +bias, act -> 16-bit pairs -> 16 TMEM columns.
+// The accumulator buffer is released (`d_empty`) as soon as the values sit in registers; the
+// destination is only waited for (`dst_free`, may be null) right before the store.
 template <int FMT, int ACT>
-__device__ __forceinline__ void drain_half(uint32_t taddr, const float* __restrict__ bias, uint8_t* panel,
-                                           int row) {
+__device__ __forceinline__ void drain32(uint32_t d_addr, const float* __restrict__ bias, uint32_t dst_addr,
+                                        uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity) {
+    uint32_t r[32];
+    tmem_ld32(d_addr, r);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(d_empty);
+    uint32_t q[16];
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        uint32_t r[32];
-        tmem_ld32(taddr + part * 32, r);
-        tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(bias + part * 32);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {       // 4 chunks of 8 columns
-            float4 ba = __ldg(b4 + 2 * c), bb = __ldg(b4 + 2 * c + 1);
-            float v0 = activate<ACT>(__uint_as_float(r[8 * c + 0]) + ba.x);
-            float v1 = activate<ACT>(__uint_as_float(r[8 * c + 1]) + ba.y);
-            float v2 = activate<ACT>(__uint_as_float(r[8 * c + 2]) + ba.z);
-            float v3 = activate<ACT>(__uint_as_float(r[8 * c + 3]) + ba.w);
-            float v4 = activate<ACT>(__uint_as_float(r[8 * c + 4]) + bb.x);
-            float v5 = activate<ACT>(__uint_as_float(r[8 * c + 5]) + bb.y);
-            float v6 = activate<ACT>(__uint_as_float(r[8 * c + 6]) + bb.z);
-            float v7 = activate<ACT>(__uint_as_float(r[8 * c + 7]) + bb.w);
-            uint4 q;
-            q.x = Cvt<FMT>::pack(v0, v1); q.y = Cvt<FMT>::pack(v2, v3);
-            q.z = Cvt<FMT>::pack(v4, v5); q.w = Cvt<FMT>::pack(v6, v7);
-            *reinterpret_cast<uint4*>(panel + panel_off(row, part * 4 + c)) = q;
-        }
+    for (int c = 0; c < 8; ++c) {
+        const float4 b = __ldg(b4 + c);
+        const float v0 = activate<ACT>(__uint_as_float(r[4 * c + 0]) + b.x);
+        const float v1 = activate<ACT>(__uint_as_float(r[4 * c + 1]) + b.y);
+        const float v2 = activate<ACT>(__uint_as_float(r[4 * c + 2]) + b.z);
+        const float v3 = activate<ACT>(__uint_as_float(r[4 * c + 3]) + b.w);
+        q[2 * c] = Cvt<FMT>::pack(v0, v1);
+        q[2 * c + 1] = Cvt<FMT>::pack(v2, v3);
     }
+    if (dst_free) { mbar_wait(dst_free, dst_parity); tc_fence_after(); }
+    tmem_st16(dst_addr, q);
+    tmem_st_wait();
+    tc_fence_before();
 }
 
-template <int HD, int FMT, int ACT>
+template <int HD, int FMT, int ACT, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams p) {
-    using S = Smem<HD>;
-    constexpr int NC = S::NC, KP = S::KP, NS = S::NS;
+    constexpr int NC = HD / 64;        // 64-column chunks of a hidden layer
+    constexpr int KP = HD / 64;        // 64-wide K panels of layer 1
+    constexpr uint32_t COL_H1 = 0, COL_D = HD / 2, COL_H2 = COL_D + 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sXA = smem + S::XA;
-    uint8_t* sH1 = smem + S::H1;
-    uint8_t* sH2 = smem + S::H2;
-    uint8_t* sW = smem + S::WR;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::BAR + S::NBAR * 8);
+    uint8_t* sXA = smem;
+    uint8_t* sW = smem + XA_BYTES;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + NBAR * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh2 = (p.parts == 1) ? 2 : 1;                    // H2 buffers (TMEM budget)
+    const uint32_t col_out = 512u - (uint32_t)p.NP;            // OUT occupies the top NP columns
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(bar + S::W_FULL + i, 1); mbar_init(bar + S::W_EMPTY + i, 1); }
+        for (int i = 0; i < NS; ++i) { mbar_init(bar + W_FULL + i, 1); mbar_init(bar + W_EMPTY + i, 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar + S::D_FULL + i, 1); mbar_init(bar + S::D_EMPTY + i, 8);
-            mbar_init(bar + S::H2_FULL + i, 4); mbar_init(bar + S::H2_EMPTY + i, 1);
+            mbar_init(bar + D_FULL + i, 1); mbar_init(bar + D_EMPTY + i, 8);
+            mbar_init(bar + H2_FULL + i, 8); mbar_init(bar + H2_EMPTY + i, 1);
         }
-        mbar_init(bar + S::H1_FULL, 8 * NC);
-        mbar_init(bar + S::OUT_FULL, 1); mbar_init(bar + S::OUT_EMPTY, 4);
-        mbar_init(bar + S::X_FULL, 4);
+        mbar_init(bar + H1_FULL, 8 * NC);
+        mbar_init(bar + OUT_FULL, 1); mbar_init(bar + OUT_EMPTY, 4);
+        mbar_init(bar + X_FULL, 4);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t w2_bytes = (uint32_t)p.NP * 128u;
+    // The CTA owns all 512 columns, so the allocation can only start at lane 0 / column 0.  Treating
+    // the base as the constant 0 keeps every MMA operand address in uniform registers (a base read
+    // back from shared memory forces a per-instruction R2UR waterfall, ~100 cycles per MMA).
+    if (*tmem_slot != 0u) { if (threadIdx.x == 0) printf("cmbpo: unexpected TMEM base %u\n", *tmem_slot); __trap(); }
+    constexpr uint32_t tmem = 0u;
+    const uint32_t w2_bytes = (uint32_t)(p.NP / p.parts) * 128u;
+    // members are visited in a CTA-dependent rotation so that the 148 CTAs do not all stream the
+    // same weight tiles at the same time (spreads the L2 traffic over E x more addresses)
+    const int e_rot = blockIdx.x % p.E;
 
     if (warp == 0) {
         // ===== weight producer: streams the per-member stage program in consumption order =====
-        if (lane == 0) {
-            uint32_t s = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                for (int e = 0; e < p.E; ++e) {
-                    const uint8_t* src = p.wpack + (unsigned long long)e * p.member_bytes;
-                    auto push = [&](uint32_t bytes) {
-                        mbar_wait(bar + S::W_EMPTY + s, ph ^ 1);
-                        mbar_expect_tx(bar + S::W_FULL + s, bytes);
-                        bulk_g2s(sW + s * PANEL, src, bytes, bar + S::W_FULL + s);
-                        src += bytes;
-                        if (++s == NS) { s = 0; ph ^= 1; }
-                    };
-                    for (int j = 0; j < NC; ++j) push(PANEL);
-                    for (int j = 0; j < NC; ++j) {
-                        for (int kp = 0; kp < KP; ++kp) push(PANEL);
-                        if (j >= 1) { push(w2_bytes); push(w2_bytes); }
+        uint32_t s = 0, ph = 0;
+        unsigned long long c_wempty = 0;
+        const long long t_begin = DBG ? clock64() : 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            for (int ei = 0; ei < p.E; ++ei) {
+                const int e = (ei + e_rot) % p.E;
+                const uint8_t* src = p.wpack + (unsigned long long)e * p.member_bytes;
+                auto push = [&](uint32_t bytes) {
+                    wait_t<DBG>(bar + W_EMPTY + s, ph ^ 1, c_wempty);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar + W_FULL + s, bytes);
+                        bulk_g2s(sW + s * STAGE, src, bytes, bar + W_FULL + s);
                     }
-                    push(w2_bytes); push(w2_bytes);
+                    src += bytes;
+                    if (++s == NS) { s = 0; ph ^= 1; }
+                };
+                for (int j = 0; j < NC; ++j) push(STAGE);
+                for (int j = 0; j < NC; ++j) {
+                    for (int kp = 0; kp < KP; ++kp) push(STAGE);
+                    if (j >= 1) for (int q = 0; q < p.parts; ++q) push(w2_bytes);
                 }
+                for (int q = 0; q < p.parts; ++q) push(w2_bytes);
             }
         }
+        if (DBG && p.dbg && lane == 0) {
+            p.dbg[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_begin);
+            p.dbg[blockIdx.x * 16 + 1] = c_wempty;
+        }
     } else if (warp == 1) {
-        // ===== MMA issuer (single thread) =====
-        if (lane == 0) {
-            const uint32_t idesc_h = idesc_f16(FMT, 128);
-            const uint32_t idesc_o = idesc_f16(FMT, p.NP);
-            const uint64_t dXA = smem_desc_sw128(smem_u32(sXA));
-            uint32_t s = 0, ph = 0, g = 0, m = 0, c1 = 0, it = 0;
-            auto next_stage = [&]() { if (++s == NS) { s = 0; ph ^= 1; } };
-            auto l2_partials = [&](int jj) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (jj == 0 && h == 0) { mbar_wait(bar + S::OUT_EMPTY, (m & 1) ^ 1); }
-                    mbar_wait(bar + S::H2_FULL + h, c1 & 1);
-                    mbar_wait(bar + S::W_FULL + s, ph);
-                    tc_fence_after();
-                    const uint64_t dA = smem_desc_sw128(smem_u32(sH2 + h * PANEL));
-                    const uint64_t dB = smem_desc_sw128(smem_u32(sW + s * PANEL));
+        // ===== MMA issuer: warp-uniform control flow, lane 0 issues every tcgen05.mma / commit =====
+        const uint32_t idesc_h = idesc_f16(FMT, 64);
+        const uint32_t idesc_o = idesc_f16(FMT, p.NP / p.parts);
+        const uint64_t dXA = smem_desc_sw128(smem_u32(sXA));
+        const uint64_t dW0 = smem_desc_sw128(smem_u32(sW));
+        uint32_t s = 0, ph = 0, g = 0, m = 0, c1 = 0, it = 0;
+        unsigned long long c_w = 0, c_d = 0, c_h1 = 0, c_h2 = 0, c_out = 0, c_x = 0;
+        const long long t_begin = DBG ? clock64() : 0;
+        auto next_stage = [&]() { if (++s == NS) { s = 0; ph ^= 1; } };
+        auto l2_partial = [&](int jj) {             // OUT += H2[chunk jj] x W2[rows of chunk jj]
+            const uint32_t hb = (nh2 == 2) ? (c1 & 1) : 0, hn = (nh2 == 2) ? (c1 >> 1) : c1;
+            if (jj == 0) wait_t<DBG>(bar + OUT_EMPTY, (m & 1) ^ 1, c_out);
+            wait_t<DBG>(bar + H2_FULL + hb, hn & 1, c_h2);
+            for (int q = 0; q < p.parts; ++q) {
+                wait_t<DBG>(bar + W_FULL + s, ph, c_w);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dB = dW0 + (uint64_t)(s * (STAGE >> 4));
+                    const uint32_t dcol = tmem + col_out + q * (p.NP / p.parts);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        mma_f16(tmem + 256, dA + 2 * ks, dB + 2 * ks, idesc_o, !(jj == 0 && h == 0 && ks == 0));
-                    mma_commit(bar + S::W_EMPTY + s);
-                    next_stage();
-                    mma_commit(bar + S::H2_EMPTY + h);
+                        mma_f16_ts(dcol, tmem + COL_H2 + hb * 32 + ks * 8, dB + 2 * ks, idesc_o, !(jj == 0 && ks == 0));
+                    mma_commit(bar + W_EMPTY + s);
                 }
-                ++c1;
-            };
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-                mbar_wait(bar + S::X_FULL, it & 1);
-                tc_fence_after();
-                for (int e = 0; e < p.E; ++e) {
-                    for (int j = 0; j < NC; ++j) {              // layer 0
-                        const uint32_t buf = g & 1, n = g >> 1;
-                        mbar_wait(bar + S::D_EMPTY + buf, (n & 1) ^ 1);
-                        mbar_wait(bar + S::W_FULL + s, ph);
-                        tc_fence_after();
-                        const uint64_t dB = smem_desc_sw128(smem_u32(sW + s * PANEL));
-                        for (int ks = 0; ks < p.KS0; ++ks)
-                            mma_f16(tmem + buf * 128, dXA + 2 * ks, dB + 2 * ks, idesc_h, ks > 0);
-                        mma_commit(bar + S::W_EMPTY + s);
-                        next_stage();
-                        mma_commit(bar + S::D_FULL + buf);
-                        ++g;
-                    }
-                    mbar_wait(bar + S::H1_FULL, m & 1);
+                __syncwarp();
+                next_stage();
+            }
+            if (elect_one()) mma_commit(bar + H2_EMPTY + hb);
+            __syncwarp();
+            ++c1;
+        };
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            wait_t<DBG>(bar + X_FULL, it & 1, c_x);
+            tc_fence_after();
+            for (int ei = 0; ei < p.E; ++ei) {
+                for (int j = 0; j < NC; ++j) {              // layer 0: D = XA x W0 chunk
+                    const uint32_t buf = g & 1, n = g >> 1;
+                    wait_t<DBG>(bar + D_EMPTY + buf, (n & 1) ^ 1, c_d);
+                    wait_t<DBG>(bar + W_FULL + s, ph, c_w);
                     tc_fence_after();
-                    for (int j = 0; j < NC; ++j) {              // layer 1 (+ layer 2 of the previous chunk)
-                        const uint32_t buf = g & 1, n = g >> 1;
-                        mbar_wait(bar + S::D_EMPTY + buf, (n & 1) ^ 1);
+                    if (elect_one()) {
+                        const uint64_t dB = dW0 + (uint64_t)(s * (STAGE >> 4));
+                        for (int ks = 0; ks < p.KS0; ++ks)
+                            mma_f16(tmem + COL_D + buf * 64, dXA + 2 * ks, dB + 2 * ks, idesc_h, ks > 0);
+                        mma_commit(bar + W_EMPTY + s);
+                        mma_commit(bar + D_FULL + buf);
+                    }
+                    __syncwarp();
+                    next_stage();
+                    ++g;
+                }
+                wait_t<DBG>(bar + H1_FULL, m & 1, c_h1);
+                tc_fence_after();
+                for (int j = 0; j < NC; ++j) {              // layer 1 (+ layer 2 of the previous chunk)
+                    const uint32_t buf = g & 1, n = g >> 1;
+                    wait_t<DBG>(bar + D_EMPTY + buf, (n & 1) ^ 1, c_d);
+                    tc_fence_after();
+#pragma unroll 2
+                    for (int kp = 0; kp < KP; ++kp) {
+                        wait_t<DBG>(bar + W_FULL + s, ph, c_w);
                         tc_fence_after();
-                        for (int kp = 0; kp < KP; ++kp) {
-                            mbar_wait(bar + S::W_FULL + s, ph);
-                            tc_fence_after();
-                            const uint64_t dA = smem_desc_sw128(smem_u32(sH1 + kp * PANEL));
-                            const uint64_t dB = smem_desc_sw128(smem_u32(sW + s * PANEL));
+                        if (elect_one()) {
+                            const uint64_t dB = dW0 + (uint64_t)(s * (STAGE >> 4));
+                            const uint32_t aT = tmem + COL_H1 + kp * 32;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
-                                mma_f16(tmem + buf * 128, dA + 2 * ks, dB + 2 * ks, idesc_h, (kp | ks) > 0);
-                            mma_commit(bar + S::W_EMPTY + s);
-                            next_stage();
+                                mma_f16_ts(tmem + COL_D + buf * 64, aT + ks * 8, dB + 2 * ks, idesc_h, (kp | ks) > 0);
+                            mma_commit(bar + W_EMPTY + s);
                         }
-                        mma_commit(bar + S::D_FULL + buf);
-                        ++g;
-                        if (j >= 1) l2_partials(j - 1);
+                        __syncwarp();
+                        next_stage();
                     }
-                    l2_partials(NC - 1);
-                    mma_commit(bar + S::OUT_FULL);
-                    ++m;
+                    if (elect_one()) mma_commit(bar + D_FULL + buf);
+                    __syncwarp();
+                    ++g;
+                    if (j >= 1) l2_partial(j - 1);
                 }
+                l2_partial(NC - 1);
+                if (elect_one()) mma_commit(bar + OUT_FULL);
+                __syncwarp();
+                ++m;
             }
+        }
+        if (DBG && p.dbg && lane == 0) {
+            unsigned long long* d = p.dbg + blockIdx.x * 16;
+            d[2] = (unsigned long long)(clock64() - t_begin);
+            d[3] = c_w; d[4] = c_d; d[5] = c_h1; d[6] = c_h2; d[7] = c_out; d[8] = c_x;
         }
     } else if (warp >= 4) {
         // ===== epilogue: 2 warpgroups x 128 threads, thread <-> row =====
@@ -226,6 +270,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         const int row = wq * 32 + lane;
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
         uint32_t g = 0, m = 0, c1 = 0;
+        unsigned long long c_dfull = 0, c_drain = 0, c_outw = 0;
+        const long long t_begin = DBG ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const long long grow = (long long)tile * 128 + row;
             if (wg == 0) {
@@ -251,43 +297,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar + S::X_FULL);
+                if (lane == 0) mbar_arrive(bar + X_FULL);
             }
-            for (int e = 0; e < p.E; ++e) {
+            for (int ei = 0; ei < p.E; ++ei) {
+                const int e = (ei + e_rot) % p.E;
                 const float* bias = p.bias + (long long)e * p.bias_stride;
-                for (int j = 0; j < NC; ++j) {                  // layer-0 chunk -> H1 panel 2j+wg
+                for (int j = 0; j < NC; ++j) {                  // layer-0 chunk -> H1 columns
                     const uint32_t buf = g & 1, n = g >> 1;
-                    mbar_wait(bar + S::D_FULL + buf, n & 1);
+                    wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
                     tc_fence_after();
-                    drain_half<FMT, ACT>(tmem + buf * 128 + wg * 64 + lane_base, bias + j * 128 + wg * 64,
-                                         sH1 + (2 * j + wg) * PANEL, row);
-                    tc_fence_before();
-                    fence_proxy_async();
+                    const long long td = DBG ? clock64() : 0;
+                    drain32<FMT, ACT>(tmem + COL_D + buf * 64 + wg * 32 + lane_base, bias + j * 64 + wg * 32,
+                                      tmem + COL_H1 + j * 32 + wg * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0);
+                    if (DBG) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(bar + S::D_EMPTY + buf); mbar_arrive(bar + S::H1_FULL); }
+                    if (lane == 0) mbar_arrive(bar + H1_FULL);
                     ++g;
                 }
-                for (int j = 0; j < NC; ++j) {                  // layer-1 chunk -> H2 half wg
+                for (int j = 0; j < NC; ++j) {                  // layer-1 chunk -> an H2 buffer
                     const uint32_t buf = g & 1, n = g >> 1;
-                    mbar_wait(bar + S::D_FULL + buf, n & 1);
-                    mbar_wait(bar + S::H2_EMPTY + wg, (c1 & 1) ^ 1);
+                    const uint32_t hb = (nh2 == 2) ? (c1 & 1) : 0, hn = (nh2 == 2) ? (c1 >> 1) : c1;
+                    wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
                     tc_fence_after();
-                    drain_half<FMT, ACT>(tmem + buf * 128 + wg * 64 + lane_base,
-                                         bias + HD + j * 128 + wg * 64, sH2 + wg * PANEL, row);
-                    tc_fence_before();
-                    fence_proxy_async();
+                    const long long td = DBG ? clock64() : 0;
+                    drain32<FMT, ACT>(tmem + COL_D + buf * 64 + wg * 32 + lane_base, bias + HD + j * 64 + wg * 32,
+                                      tmem + COL_H2 + hb * 32 + wg * 16 + lane_base, bar + D_EMPTY + buf,
+                                      bar + H2_EMPTY + hb, (hn & 1) ^ 1);
+                    if (DBG) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(bar + S::D_EMPTY + buf); mbar_arrive(bar + S::H2_FULL + wg); }
+                    if (lane == 0) mbar_arrive(bar + H2_FULL + hb);
                     ++g; ++c1;
                 }
-                if (wg == 0) {                                   // OUT -> global raw outputs
-                    mbar_wait(bar + S::OUT_FULL, m & 1);
+                if (wg == (int)(m & 1)) {                        // OUT -> global raw outputs (warpgroups alternate)
+                    wait_t<DBG>(bar + OUT_FULL, m & 1, c_outw);
                     tc_fence_after();
                     float* orow = p.out + (long long)e * p.out_member_stride + grow * p.Nout;
                     const float* b2 = bias + 2 * HD;
                     for (int c0 = 0; c0 < p.NP; c0 += 16) {
                         uint32_t r[16];
-                        tmem_ld16(tmem + 256 + c0 + lane_base, r);
+                        tmem_ld16(tmem + col_out + c0 + lane_base, r);
                         tmem_ld_wait();
                         if (grow < p.N) {
 #pragma unroll
@@ -297,10 +345,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar + S::OUT_EMPTY);
+                    if (lane == 0) mbar_arrive(bar + OUT_EMPTY);
                 }
                 ++m;
             }
+        }
+        if (DBG && p.dbg && warp == 4 && lane == 0) {
+            unsigned long long* d = p.dbg + blockIdx.x * 16;
+            d[9] = (unsigned long long)(clock64() - t_begin);
+            d[10] = c_dfull; d[12] = c_drain; d[13] = c_outw;
         }
     }
     tc_fence_before();
@@ -346,29 +399,36 @@ __global__ void pack_bias_kernel(const float* b0, const float* b1, const float* 
     }
 }
 
-std::vector<Stage> stage_program(int HD, int NP, unsigned long long* total) {
-    const int NC = HD / 128, KP = HD / 64;
+struct OutShape { int NP, parts; };
+OutShape out_shape(int Nout) {
+    if (Nout <= 64) return {((Nout + 15) / 16) * 16, 1};
+    return {((Nout + 31) / 32) * 32, 2};       // two N-halves, each a multiple of 16
+}
+
+// the order in which the MMA warp consumes weight tiles (must match the kernel's loops)
+std::vector<Stage> stage_program(int HD, int NP, int parts, unsigned long long* total) {
+    const int NC = HD / 64, KP = HD / 64, NPp = NP / parts;
     std::vector<Stage> v;
     unsigned long long off = 0;
     auto add = [&](int layer, int n0, int k0, int rows) {
         v.push_back(Stage{layer, n0, k0, rows, off});
         off += (unsigned long long)rows * 128;
     };
-    for (int j = 0; j < NC; ++j) add(0, j * 128, 0, 128);
+    auto add_w2 = [&](int chunk) { for (int q = 0; q < parts; ++q) add(2, q * NPp, chunk * 64, NPp); };
+    for (int j = 0; j < NC; ++j) add(0, j * 64, 0, 64);
     for (int j = 0; j < NC; ++j) {
-        for (int kp = 0; kp < KP; ++kp) add(1, j * 128, kp * 64, 128);
-        if (j >= 1) { add(2, 0, (j - 1) * 128, NP); add(2, 0, (j - 1) * 128 + 64, NP); }
+        for (int kp = 0; kp < KP; ++kp) add(1, j * 64, kp * 64, 64);
+        if (j >= 1) add_w2(j - 1);
     }
-    add(2, 0, (NC - 1) * 128, NP); add(2, 0, (NC - 1) * 128 + 64, NP);
+    add_w2(NC - 1);
     *total = off;
     return v;
 }
 
-template <int HD, int FMT, int ACT>
+template <int HD, int FMT, int ACT, bool DBG>
 int launch_tc(cmbpo_ctx* ctx, const TcParams& p) {
-    using S = Smem<HD>;
-    const int smem = S::TOTAL + 1024;
-    auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT>;
+    const int smem = SMEM_TOTAL + 1024;
+    auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT, DBG>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = p.ntiles < ctx->sm_count ? p.ntiles : ctx->sm_count;
     kern<<<grid, NTHREADS, smem, ctx->stream>>>(p);
@@ -379,8 +439,8 @@ int launch_tc(cmbpo_ctx* ctx, const TcParams& p) {
 
 template <int HD, int FMT>
 int launch_tc_act(cmbpo_ctx* ctx, const TcParams& p, int act) {
-    if (act == CMBPO_ACT_SWISH) return launch_tc<HD, FMT, CMBPO_ACT_SWISH>(ctx, p);
-    return launch_tc<HD, FMT, CMBPO_ACT_TANH>(ctx, p);
+    if (act == CMBPO_ACT_SWISH) return launch_tc<HD, FMT, CMBPO_ACT_SWISH, false>(ctx, p);
+    return launch_tc<HD, FMT, CMBPO_ACT_TANH, false>(ctx, p);
 }
 
 template <int FMT>
@@ -404,9 +464,9 @@ bool ens_tc_supported(const Net& n) {
 // pack both 16-bit formats once per weight upload
 int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
     const int HD = net.dims[1], K0 = net.dims[0], Nout = net.dims[3];
-    const int NP = ((Nout + 15) / 16) * 16;
+    const OutShape os = out_shape(Nout);
     unsigned long long member_bytes = 0;
-    std::vector<Stage> prog = stage_program(HD, NP, &member_bytes);
+    std::vector<Stage> prog = stage_program(HD, os.NP, os.parts, &member_bytes);
     Stage* d_prog;
     CUDA_TRY(cudaMalloc(&d_prog, prog.size() * sizeof(Stage)));
     CUDA_TRY(cudaMemcpyAsync(d_prog, prog.data(), prog.size() * sizeof(Stage), cudaMemcpyHostToDevice, ctx->stream));
@@ -421,8 +481,8 @@ int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
             pack_weights_kernel<1><<<grid, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_prog,
                                                                (int)prog.size(), member_bytes, (uint8_t*)net.tc_pack[prec]);
     }
-    CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)net.E * (2 * HD + NP) * sizeof(float)));
-    pack_bias_kernel<<<net.E, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, Nout, NP, net.tc_bias);
+    CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)net.E * (2 * HD + os.NP) * sizeof(float)));
+    pack_bias_kernel<<<net.E, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, Nout, os.NP, net.tc_bias);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaFree(d_prog));
     CUDA_TRY(cudaGetLastError());
@@ -434,17 +494,40 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     CMBPO_CHECK(net.tc_pack[precision], "tcgen05 weights not packed");
     if (N <= 0) return 0;
     const int HD = net.dims[1];
+    const OutShape os = out_shape(net.dims[3]);
     TcParams p;
     p.wpack = (const uint8_t*)net.tc_pack[precision];
     p.member_bytes = net.tc_pack_bytes[precision];
     p.Nout = net.dims[3];
-    p.NP = ((p.Nout + 15) / 16) * 16;
+    p.NP = os.NP; p.parts = os.parts;
     p.bias = net.tc_bias; p.bias_stride = 2 * HD + p.NP;
     p.E = net.E; p.K0 = net.dims[0]; p.KS0 = (p.K0 + 15) / 16;
     p.x = x; p.N = N; p.ldx = net.dims[0];
     p.mu_in = net.has_in ? net.mu_in : nullptr; p.sig_in = net.sig_in;
     p.out = out_raw; p.out_member_stride = (long long)N * p.Nout;
     p.ntiles = (int)((N + 127) / 128);
+    p.dbg = nullptr;
+    static const char* dbg_env = getenv("CMBPO_TC_DEBUG");
+    if (dbg_env && HD == 512 && net.acts[0] == CMBPO_ACT_SWISH && precision == CMBPO_PREC_FP16) {
+        // protocol timing: per-CTA cycle counters printed once per launch (debug aid, off by default)
+        unsigned long long* d;
+        if (cmbpo_ws_get(ctx, 1, (size_t)ctx->sm_count * 16 * 8, (void**)&d)) return 1;
+        CUDA_TRY(cudaMemsetAsync(d, 0, (size_t)ctx->sm_count * 16 * 8, ctx->stream));
+        p.dbg = d;
+        if (launch_tc<512, 0, CMBPO_ACT_SWISH, true>(ctx, p)) return 1;
+        std::vector<unsigned long long> h((size_t)ctx->sm_count * 16);
+        CUDA_TRY(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        const char* names[14] = {"prod_total", "prod_wait_wempty", "mma_total", "mma_wait_wfull", "mma_wait_dempty",
+                                 "mma_wait_h1", "mma_wait_h2full", "mma_wait_outempty", "mma_wait_x", "epi_total",
+                                 "epi_wait_dfull", "-", "epi_drain", "epi_wait_outfull"};
+        for (int k = 0; k < 14; ++k) {
+            double sum = 0; int n = 0;
+            for (int b = 0; b < ctx->sm_count && b < p.ntiles; ++b) { sum += (double)h[(size_t)b * 16 + k]; ++n; }
+            fprintf(stderr, "tcdbg %-18s %12.0f cycles/CTA\n", names[k], sum / (n ? n : 1));
+        }
+        return 0;
+    }
     if (precision == CMBPO_PREC_FP16) return launch_tc_hd<0>(ctx, p, HD, net.acts[0]);
     return launch_tc_hd<1>(ctx, p, HD, net.acts[0]);
 }

@@ -88,7 +88,21 @@ struct RawDyn {
     __device__ float operator()(int e, int c) const { return raw[((int64_t)e * N + p) * W + c]; }
 };
 
-// ---- single-step FakeEnv.step ------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Dense row kernels: one thread per (row, obs dimension).  A block of 256 threads covers
+// RB = 256 / O consecutive rows, so every lane is busy for any O (17, 29, 47 ...).  Phase 1 is the
+// per-dimension arithmetic (env_dim, row_math.cuh); phase 2 runs on the row-owner thread (dim 0):
+// ordered sums over the dimensions, statics, sampler rules, scalar writes; phase 3 writes the
+// vector fields with all threads.
+// ------------------------------------------------------------------------------------------------
+constexpr int ROW_THREADS = 256;
+
+struct RowShared {
+    float kl[ROW_THREADS], epv[ROW_THREADS], nx[ROW_THREADS];
+    unsigned char fin[ROW_THREADS], cut[ROW_THREADS];
+    double stats[4];
+};
+
 struct EnvStepArgs {
     int64_t N; int O, A;
     EnvRowCfg c; int n_elite;
@@ -99,37 +113,40 @@ struct EnvStepArgs {
     double* dkl_sum;   // 1 double accumulator
 };
 
-__global__ void env_step_kernel(EnvStepArgs a) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double dk = 0.0;
-    if (p < a.N) {
-        float obs[CMBPO_MAX_OBS], nx[CMBPO_MAX_OBS];
-        for (int o = 0; o < a.O; ++o) obs[o] = a.obs[p * a.O + o];
-        const int64_t gid = a.path_ids ? (int64_t)a.path_ids[p] : p;
-        int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, gid, a.step, a.n_elite);
-        float seps[CMBPO_MAX_OBS];
-        const float* sp = nullptr;
-        if (!a.c.deterministic && a.state_eps) {
-            for (int o = 0; o < a.O; ++o) seps[o] = a.state_eps[p * a.O + o];
-            sp = seps;
-        }
-        RawDyn raw{a.raw, a.N, 2 * a.c.D, p};
-        EnvRowOut r = fakeenv_row(a.c, raw, obs, pos, sp, nx, a.ep_var ? a.ep_var + p * a.O : nullptr);
-        for (int o = 0; o < a.O; ++o) a.next_obs[p * a.O + o] = nx[o];
-        a.rew[p] = r.rew; a.cost[p] = r.cost; a.term[p] = r.term ? 1 : 0;
-        a.dkl_path[p] = r.dkl_path;
-        dk = (double)r.dkl_path;
-    }
-    // ensemble_dkl_mean (fake_env.py:114): block partial -> one atomic per block
-    for (int o = 16; o > 0; o >>= 1) dk += __shfl_down_sync(0xffffffffu, dk, o);
-    __shared__ double sh[8];
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dk;
+__global__ void __launch_bounds__(ROW_THREADS) env_step_kernel(EnvStepArgs a) {
+    __shared__ RowShared sh;
+    const int O = a.O, RB = ROW_THREADS / O;
+    const int rb = threadIdx.x / O, dim = threadIdx.x - rb * O;
+    if (threadIdx.x == 0) sh.stats[0] = 0.0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[w];
-        atomicAdd(a.dkl_sum, s);
+    for (int64_t base = (int64_t)blockIdx.x * RB; base < a.N; base += (int64_t)gridDim.x * RB) {
+        const int64_t p = base + rb;
+        const bool active = rb < RB && p < a.N;
+        int member = 0;
+        if (active) {
+            const int64_t gid = a.path_ids ? (int64_t)a.path_ids[p] : p;
+            const int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, gid, a.step, a.n_elite);
+            member = a.c.elite[pos];
+            const float eps = (!a.c.deterministic && a.state_eps) ? a.state_eps[p * O + dim] : 1.0f;
+            RawDyn raw{a.raw, a.N, 2 * a.c.D, p};
+            EnvDimOut d = env_dim(a.c, raw, dim, member, a.obs[p * O + dim], eps);
+            sh.kl[threadIdx.x] = d.kl; sh.epv[threadIdx.x] = d.epv; sh.nx[threadIdx.x] = d.nx;
+            sh.fin[threadIdx.x] = isfinite(d.nx) ? 1 : 0;
+            a.next_obs[p * O + dim] = d.nx;
+            if (a.ep_var) a.ep_var[p * O + dim] = d.epv;
+        }
+        __syncthreads();
+        if (active && dim == 0) {
+            RawDyn raw{a.raw, a.N, 2 * a.c.D, p};
+            EnvRowOut r = env_row_finish(a.c, raw, member, sh.kl + rb * O, sh.epv + rb * O, sh.nx + rb * O,
+                                         sh.fin + rb * O);
+            a.rew[p] = r.rew; a.cost[p] = r.cost; a.term[p] = r.term ? 1 : 0;
+            a.dkl_path[p] = r.dkl_path;
+            atomicAdd(&sh.stats[0], (double)r.dkl_path);
+        }
+        __syncthreads();
     }
+    if (threadIdx.x == 0 && sh.stats[0] != 0.0) atomicAdd(a.dkl_sum, sh.stats[0]);   // fake_env.py:114
 }
 
 __global__ void finish_mean_kernel(const double* sum, int64_t n, float* out) {
@@ -152,69 +169,80 @@ struct StepArgs {
     cmbpo_rollout_bufs b;
 };
 
-__global__ void rollout_step_kernel(StepArgs a) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double fed = 0, dsum = 0, stored = 0, evsum = 0;
-    if (p < a.B && a.alive[p]) {
-        const int O = a.O, A = a.A, t = a.t;
-        float obs[CMBPO_MAX_OBS], nx[CMBPO_MAX_OBS], seps[CMBPO_MAX_OBS];
-        for (int o = 0; o < O; ++o) obs[o] = a.cur_obs[p * O + o];
-        const int64_t gid = a.path_base + p;
-        int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, gid, t, a.n_elite);
-        const float* sp = nullptr;
-        if (!a.c.deterministic) {
-            for (int o = 0; o < O; ++o)
-                seps[o] = a.state_eps ? a.state_eps[p * O + o]
-                                      : philox_normal(a.seed, gid, t, RNG_STREAM_STATE, o);
-            sp = seps;
+__global__ void __launch_bounds__(ROW_THREADS) rollout_step_kernel(StepArgs a) {
+    __shared__ RowShared sh;
+    const int O = a.O, A = a.A, t = a.t, RB = ROW_THREADS / O;
+    const int rb = threadIdx.x / O, dim = threadIdx.x - rb * O;
+    if (threadIdx.x < 4) sh.stats[threadIdx.x] = 0.0;
+    __syncthreads();
+    for (int64_t base = (int64_t)blockIdx.x * RB; base < a.B; base += (int64_t)gridDim.x * RB) {
+        const int64_t p = base + rb;
+        const bool active = rb < RB && p < a.B && a.alive[p];
+        int member = 0;
+        float obs_d = 0.f;
+        if (active) {
+            const int64_t gid = a.path_base + p;
+            const int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, gid, t, a.n_elite);
+            member = a.c.elite[pos];
+            float eps = 1.0f;
+            if (!a.c.deterministic)
+                eps = a.state_eps ? a.state_eps[p * O + dim] : philox_normal(a.seed, gid, t, RNG_STREAM_STATE, dim);
+            obs_d = a.cur_obs[p * O + dim];
+            RawDyn raw{a.raw, a.B, 2 * a.c.D, p};
+            EnvDimOut d = env_dim(a.c, raw, dim, member, obs_d, eps);
+            sh.kl[threadIdx.x] = d.kl; sh.epv[threadIdx.x] = d.epv; sh.nx[threadIdx.x] = d.nx;
+            sh.fin[threadIdx.x] = isfinite(d.nx) ? 1 : 0;
         }
-        RawDyn raw{a.raw, a.B, 2 * a.c.D, p};
-        EnvRowOut r = fakeenv_row(a.c, raw, obs, pos, sp, nx, nullptr);
-        fed = 1; dsum = (double)r.dkl_path;
-        const float v = a.v[p], vc = a.vc[p];
-        // uncertainty cut-off BEFORE the step is stored (model_sampler.py:275-290)
-        const double next_dkl = a.b.cum_dkl[p] + (double)r.dkl_path;
-        if (a.uncertainty && next_dkl >= a.dkl_lim) {
-            a.alive[p] = 0;
-            a.b.end_reason[p] = CMBPO_END_UNCERTAIN;
-            a.b.last_val[p] = v; a.b.last_cval[p] = vc;      // V(s_t), VC(s_t): model_sampler.py:401-407
-        } else {
-            // ModelBuffer.store_multiple (modelbuffer.py:114-135), time-major
-            const int64_t row = (int64_t)t * a.B + p;
-            for (int o = 0; o < O; ++o) { a.b.obs[row * O + o] = obs[o]; a.b.nextobs[row * O + o] = nx[o]; }
-            for (int i = 0; i < A; ++i) { a.b.act[row * A + i] = a.pi[p * A + i]; a.b.mu[row * A + i] = a.mu[p * A + i]; }
-            a.b.rew[row] = r.rew; a.b.val[row] = v; a.b.cost[row] = r.cost; a.b.cval[row] = vc;
-            a.b.logp[row] = a.logp[p]; a.b.dyn_error[row] = r.ep_var_mean; a.b.dkl[row] = r.dkl_path;
-            a.b.term[row] = r.term ? 1 : 0;
-            a.b.length[p] = t + 1;
-            a.b.cum_dkl[p] = next_dkl;                       // model_sampler.py:332
-            a.b.path_return[p] += (double)r.rew;             // :317-318
-            a.b.path_cost[p] += (double)r.cost;
-            stored = 1; evsum = (double)r.ep_var_sum;
-            for (int o = 0; o < O; ++o) a.cur_obs[p * O + o] = nx[o];   // :350
-            if (t >= a.last_storable) {                      // path_length >= max_path_length-1 (:352)
-                a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_HORIZON; a.pending[p] = 3;
-            } else if (r.term) {                             // env terminal (:357-364): V boot 0, VC boot VC(s')
-                a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_TERMINAL;
-                a.b.last_val[p] = 0.f; a.pending[p] = 2;
+        __syncthreads();
+        if (active && dim == 0) {
+            RawDyn raw{a.raw, a.B, 2 * a.c.D, p};
+            EnvRowOut r = env_row_finish(a.c, raw, member, sh.kl + rb * O, sh.epv + rb * O, sh.nx + rb * O,
+                                         sh.fin + rb * O);
+            const float v = a.v[p], vc = a.vc[p];
+            // uncertainty cut-off BEFORE the step is stored (model_sampler.py:275-290)
+            const double next_dkl = a.b.cum_dkl[p] + (double)r.dkl_path;
+            const bool cut = a.uncertainty && next_dkl >= a.dkl_lim;
+            sh.cut[rb] = cut ? 1 : 0;
+            atomicAdd(&sh.stats[0], 1.0); atomicAdd(&sh.stats[1], (double)r.dkl_path);
+            if (cut) {
+                a.alive[p] = 0;
+                a.b.end_reason[p] = CMBPO_END_UNCERTAIN;
+                a.b.last_val[p] = v; a.b.last_cval[p] = vc;      // V(s_t), VC(s_t): model_sampler.py:401-407
+            } else {
+                const int64_t row = (int64_t)t * a.B + p;          // ModelBuffer.store_multiple, time-major
+                a.b.rew[row] = r.rew; a.b.val[row] = v; a.b.cost[row] = r.cost; a.b.cval[row] = vc;
+                a.b.logp[row] = a.logp[p]; a.b.dyn_error[row] = r.ep_var_mean; a.b.dkl[row] = r.dkl_path;
+                a.b.term[row] = r.term ? 1 : 0;
+                a.b.length[p] = t + 1;
+                a.b.cum_dkl[p] = next_dkl;                        // model_sampler.py:332
+                a.b.path_return[p] += (double)r.rew;              // :317-318
+                a.b.path_cost[p] += (double)r.cost;
+                atomicAdd(&sh.stats[2], 1.0); atomicAdd(&sh.stats[3], (double)r.ep_var_sum);
+                if (t >= a.last_storable) {                       // path_length >= max_path_length-1 (:352)
+                    a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_HORIZON; a.pending[p] = 3;
+                } else if (r.term) {                              // env terminal (:357-364)
+                    a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_TERMINAL;
+                    a.b.last_val[p] = 0.f; a.pending[p] = 2;
+                }
             }
         }
+        __syncthreads();
+        if (active && !sh.cut[rb]) {
+            const int64_t row = (int64_t)t * a.B + p;
+            const float nx = sh.nx[threadIdx.x];
+            a.b.obs[row * O + dim] = obs_d;
+            a.b.nextobs[row * O + dim] = nx;
+            a.cur_obs[p * O + dim] = nx;                          // model_sampler.py:350
+            for (int i = dim; i < A; i += O) {
+                a.b.act[row * A + i] = a.pi[p * A + i];
+                a.b.mu[row * A + i] = a.mu[p * A + i];
+            }
+        }
+        __syncthreads();
     }
     // per-step statistics: rows fed, sum dkl, rows stored, sum ep_var
-    double vals[4] = {fed, dsum, stored, evsum};
-    __shared__ double sh[4][8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        double x = vals[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        double s = 0;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
-        if (s != 0.0) atomicAdd(a.b.step_stats + (int64_t)a.t * 4 + threadIdx.x, s);
-    }
+    if (threadIdx.x < 4 && sh.stats[threadIdx.x] != 0.0)
+        atomicAdd(a.b.step_stats + (int64_t)a.t * 4 + threadIdx.x, sh.stats[threadIdx.x]);
 }
 
 __global__ void rollout_init_kernel(int64_t B, int O, const float* start, float* cur, uint8_t* alive,
@@ -339,7 +367,7 @@ extern "C" int cmbpo_fakeenv_step(cmbpo_ctx* ctx, const cmbpo_env_cfg* cfg, cons
     a.seed = seed; a.step = step;
     a.next_obs = next_obs; a.rew = rew; a.cost = cost; a.term = term; a.dkl_path = dkl_path;
     a.ep_var = ep_var; a.dkl_sum = dsum;
-    env_step_kernel<<<cdiv(N, 128), 128, 0, ctx->stream>>>(a);
+    env_step_kernel<<<min(cdiv(N, ROW_THREADS / O), ctx->sm_count * 16), ROW_THREADS, 0, ctx->stream>>>(a);
     if (dkl_mean_out) finish_mean_kernel<<<1, 32, 0, ctx->stream>>>(dsum, N, dkl_mean_out);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -382,7 +410,10 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
         pa.path_base = cfg->path_id_base; pa.seed = cfg->seed; pa.step = t;
         pa.alive = alive; pa.pi = pi; pa.logp = logp; pa.mu = mu; pa.vout = v; pa.vcout = vc;
         pa.xin = xin; pa.pending = pending; pa.last_val = bufs->last_val; pa.last_cval = bufs->last_cval;
-        if (policy_forward(ctx, pa, !last, cfg->precision)) return 1;
+        {
+            ProfScope prof(ctx, CMBPO_PROF_POLICY);
+            if (policy_forward(ctx, pa, !last, cfg->precision)) return 1;
+        }
         if (last) break;
         if (ens_forward(ctx, dyn, xin, B, false, raw, cfg->precision)) return 1;
         StepArgs sa = {};
@@ -395,7 +426,10 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
         sa.elite_pos = bufs->elite_pos ? bufs->elite_pos + (size_t)t * B : nullptr;
         sa.state_eps = bufs->state_eps ? bufs->state_eps + (size_t)t * B * O : nullptr;
         sa.b = *bufs;
-        rollout_step_kernel<<<cdiv(B, 128), 128, 0, ctx->stream>>>(sa);
+        {
+            ProfScope prof(ctx, CMBPO_PROF_STEP);
+            rollout_step_kernel<<<min(cdiv(B, ROW_THREADS / O), ctx->sm_count * 16), ROW_THREADS, 0, ctx->stream>>>(sa);
+        }
         ctx->launches++;
     }
     rollout_final_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, O, cur, alive, *bufs, v, vc);

@@ -139,89 +139,6 @@ struct EnvRowOut {
     bool term;
 };
 
-template <class Raw, int MAXO>
-__device__ inline EnvRowOut fakeenv_row(const EnvRowCfg& c, Raw raw, const float (&obs)[MAXO],
-                                        int elite_pos, const float* state_eps /*[O] or null*/,
-                                        float (&next_obs)[MAXO], float* ep_var_out /*[O] or null*/) {
-    const int O = c.O, E = c.E;
-    const int member = c.elite[elite_pos];
-    float kl[MAXO], epv[MAXO];
-    const float den = (float)((double)(E * (E - 1)) + 1e-10);   // pens/utils.py:56
-    for (int o = 0; o < O; ++o) {
-        float nd[CMBPO_MAX_E], ls[CMBPO_MAX_E], vr[CMBPO_MAX_E];
-        const float sg = c.sig_out[o], mu = c.mu_out[o], l2s = c.l2s_out[o];
-        float sel = 0.f;
-#pragma unroll
-        for (int e = 0; e < CMBPO_MAX_E; ++e) {
-            if (e < E) {
-                float mean = __fadd_rn(__fmul_rn(sg, raw(e, o)), mu);           // pe.py:815-821
-                float logvar = __fadd_rn(l2s, raw(e, c.D + o));                  // pe.py:826-828
-                float var = expf(logvar);                                        // pe.py:833
-                float sd = sqrtf(var);                                           // fake_env.py:104
-                float x = mean;
-                if (!c.deterministic) {                                          // fake_env.py:105-106
-                    float m = state_eps ? state_eps[o] : 1.0f;
-                    x = __fadd_rn(mean, __fmul_rn(sd, m));
-                }
-                nd[e] = x;
-                float l = logf(sd);                                              // pens/utils.py:46-47
-                l = fminf(fmaxf(l, -100.0f), 1e8f);
-                ls[e] = l;
-                vr[e] = expf(__fmul_rn(2.0f, l));                                // pens/utils.py:20
-                if (e == member) sel = x;
-            }
-        }
-        // np.var over the member axis (fake_env.py:112): sequential sums, true divides
-        float s = 0.f;
-#pragma unroll
-        for (int e = 0; e < CMBPO_MAX_E; ++e) if (e < E) s = (e == 0) ? nd[0] : __fadd_rn(s, nd[e]);
-        float m = __fdiv_rn(s, (float)E);
-        float q = 0.f;
-#pragma unroll
-        for (int e = 0; e < CMBPO_MAX_E; ++e) if (e < E) {
-            float d = __fsub_rn(nd[e], m);
-            float d2 = __fmul_rn(d, d);
-            q = (e == 0) ? d2 : __fadd_rn(q, d2);
-        }
-        epv[o] = __fdiv_rn(q, (float)E);
-        // average_dkl (pens/utils.py:30-57): all ordered pairs, i outer / j inner
-        float acc = 0.f;
-        bool first = true;
-#pragma unroll
-        for (int i = 0; i < CMBPO_MAX_E; ++i) {
-#pragma unroll
-            for (int j = 0; j < CMBPO_MAX_E; ++j) {
-                if (i < E && j < E) {
-                    float dm = __fsub_rn(nd[j], nd[i]);
-                    float num = __fadd_rn(__fmul_rn(dm, dm), vr[i]);
-                    float ratio = __fdiv_rn(num, __fadd_rn(vr[j], 1e-10f));
-                    float pre = __fsub_rn(__fadd_rn(__fmul_rn(0.5f, __fsub_rn(ratio, 1.0f)), ls[j]), ls[i]);
-                    // np.clip(pre, 0, 1e10): nan propagates
-                    float k = (pre != pre) ? pre : fminf(fmaxf(pre, 0.0f), 1e10f);
-                    acc = first ? k : __fadd_rn(acc, k);
-                    first = false;
-                }
-            }
-        }
-        kl[o] = __fdiv_rn(acc, den);
-        next_obs[o] = c.predicts_delta ? __fadd_rn(sel, obs[o]) : sel;               // fake_env.py:125-131
-        if (ep_var_out) ep_var_out[o] = epv[o];
-    }
-    EnvRowOut r;
-    r.dkl_path = __fdiv_rn(np_sum_f32(kl, O), (float)O);                         // fake_env.py:113
-    float es = np_sum_f32(epv, O);
-    r.ep_var_sum = es;
-    r.ep_var_mean = __fdiv_rn(es, (float)O);                                     // model_sampler.py:343
-    apply_statics(c.term_id, c.cost_id, next_obs, O, r.term, r.cost);            // fake_env.py:134-146
-    int rcol = c.D - 1;
-    if (c.predicts_cost) {                                                       // fake_env.py:139-142
-        r.cost = __fadd_rn(__fmul_rn(c.sig_out[rcol], raw(member, rcol)), c.mu_out[rcol]);
-        rcol -= 1;
-    }
-    r.rew = __fadd_rn(__fmul_rn(c.sig_out[rcol], raw(member, rcol)), c.mu_out[rcol]);  // :148-151
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------
 // Gaussian actor head for one row (ac_network.py:105-111, 46-48)
 // ------------------------------------------------------------------------------------------
@@ -239,4 +156,136 @@ __device__ inline float actor_row(const float (&mu)[MAXA], const float* log_std,
         terms[a] = __fmul_rn(-0.5f, t);                                          // ac_network.py:47
     }
     return np_sum_f32(terms, A);
+}
+
+// numpy pairwise-sum order over an array in memory (see np_sum_f32)
+__device__ inline float np_sum_ptr(const float* a, int n) {
+    if (n < 8) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, a[i]);
+        return s;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n & 7); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+    }
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) s = __fadd_rn(s, a[i]);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// FakeEnv.step split per (row, obs dimension) -- the unit of work of the dense row kernels.
+// env_dim: everything that only needs the E members' outputs for ONE dimension
+// (fake_env.py:104-113 for that column); env_row_finish: the reductions over dimensions, statics,
+// reward (fake_env.py:113-153).
+//
+// Arithmetic notes.  mean / next_obs / ep_var follow the reference's float32 op order exactly.
+// The KL term uses two algebraic shortcuts that change results only at rounding level (tests
+// state rtol 2e-3 on dkl): log_std = logvar/2 and exp(2 log_std) = var instead of
+// log(sqrt(exp(logvar))) round trips (with the reference's clip behaviour kept for var == 0 / inf),
+// and multiplication by a per-member reciprocal instead of 49 IEEE divisions.
+// ------------------------------------------------------------------------------------------
+struct EnvDimOut { float kl, epv, nx; };
+
+template <class Raw>
+__device__ inline EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o, int member, float obs_o, float eps) {
+    const int E = c.E;
+    float nd[CMBPO_MAX_E], ls[CMBPO_MAX_E], vr[CMBPO_MAX_E], rv[CMBPO_MAX_E];
+    const float sg = c.sig_out[o], mu = c.mu_out[o], l2s = c.l2s_out[o];
+    float sel = 0.f;
+#pragma unroll
+    for (int e = 0; e < CMBPO_MAX_E; ++e) {
+        if (e < E) {
+            const float mean = __fadd_rn(__fmul_rn(sg, raw(e, o)), mu);          // pe.py:815-821
+            const float logvar = __fadd_rn(l2s, raw(e, c.D + o));                // pe.py:826-828
+            const float var = __expf(logvar);                                    // pe.py:833
+            float x = mean;
+            if (!c.deterministic) x = __fadd_rn(mean, __fmul_rn(sqrtf(var), eps));   // fake_env.py:104-106
+            nd[e] = x;
+            // log_std = clip(log(sqrt(var)), -100, 1e8) (pens/utils.py:46-47); var = exp(2 log_std)
+            float l = 0.5f * logvar, v2 = var;
+            if (var == 0.f) { l = -100.f; v2 = 0.f; }                            // log(0) = -inf -> -100 -> exp(-200) = 0
+            else if (isinf(var)) { l = 1e8f; }                                   // clip at 1e8 -> exp(2e8) = inf
+            if (logvar != logvar) { l = logvar; v2 = logvar; }
+            ls[e] = l; vr[e] = v2;
+            rv[e] = __frcp_rn(__fadd_rn(v2, 1e-10f));
+            if (e == member) sel = x;
+        }
+    }
+    // np.var over the member axis (fake_env.py:112): sequential sums, true divides
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < CMBPO_MAX_E; ++e) if (e < E) s = (e == 0) ? nd[0] : __fadd_rn(s, nd[e]);
+    const float m = __fdiv_rn(s, (float)E);
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < CMBPO_MAX_E; ++e) if (e < E) {
+        const float d = __fsub_rn(nd[e], m);
+        const float d2 = __fmul_rn(d, d);
+        q = (e == 0) ? d2 : __fadd_rn(q, d2);
+    }
+    EnvDimOut out;
+    out.epv = __fdiv_rn(q, (float)E);
+    // average_dkl (pens/utils.py:30-57): all ordered pairs, i outer / j inner
+    float acc = 0.f;
+    bool first = true;
+#pragma unroll
+    for (int i = 0; i < CMBPO_MAX_E; ++i) {
+#pragma unroll
+        for (int j = 0; j < CMBPO_MAX_E; ++j) {
+            if (i < E && j < E) {
+                const float dm = __fsub_rn(nd[j], nd[i]);
+                const float ratio = __fmul_rn(__fadd_rn(__fmul_rn(dm, dm), vr[i]), rv[j]);
+                const float pre = __fsub_rn(__fadd_rn(__fmul_rn(0.5f, __fsub_rn(ratio, 1.0f)), ls[j]), ls[i]);
+                const float k = (pre != pre) ? pre : fminf(fmaxf(pre, 0.0f), 1e10f);   // np.clip keeps nan
+                acc = first ? k : __fadd_rn(acc, k);
+                first = false;
+            }
+        }
+    }
+    out.kl = __fdiv_rn(acc, (float)((double)(E * (E - 1)) + 1e-10));             // pens/utils.py:56
+    out.nx = c.predicts_delta ? __fadd_rn(sel, obs_o) : sel;                     // fake_env.py:125-131
+    return out;
+}
+
+// row-owner part: ordered reductions over the O dimensions (numpy order), statics, reward
+template <class Raw>
+__device__ inline EnvRowOut env_row_finish(const EnvRowCfg& c, Raw raw, int member, const float* kl,
+                                           const float* epv, const float* nx, const unsigned char* fin) {
+    const int O = c.O;
+    EnvRowOut r;
+    r.dkl_path = __fdiv_rn(np_sum_ptr(kl, O), (float)O);                         // fake_env.py:113
+    const float es = np_sum_ptr(epv, O);
+    r.ep_var_sum = es;
+    r.ep_var_mean = __fdiv_rn(es, (float)O);                                     // model_sampler.py:343
+    bool all_finite = true;
+    for (int o = 0; o < O; ++o) all_finite = all_finite && fin[o];
+    auto notdone = [&]() {                                                       // statics.py:24-27
+        const float z = nx[0], q1 = nx[2], q2 = nx[3];
+        const float zrot = __fsub_rn(1.0f, __fmul_rn(2.0f, __fadd_rn(__fmul_rn(q1, q1), __fmul_rn(q2, q2))));
+        const bool flags = all_finite && (z >= 0.2f) && (z <= 1.0f);
+        return __fmul_rn(flags ? 1.0f : 0.0f, zrot) >= -0.7f;
+    };
+    r.term = (c.term_id == CMBPO_TERM_ANTSAFE) ? !notdone() : false;             // statics.py:17-31
+    if (c.cost_id == CMBPO_COST_HCS) {                                           // statics.py:10-15
+        r.cost = (fabsf(__fmul_rn(nx[O - 1], 10.0f)) < 2.0f) ? 1.0f : 0.0f;
+    } else if (c.cost_id == CMBPO_COST_ANTSAFE) {                                // statics.py:33-53
+        const float cc = (!notdone() ? 1.0f : 0.0f) + ((fabsf(nx[O - 1]) > 3.2f) ? 1.0f : 0.0f);
+        r.cost = fminf(fmaxf(cc, 0.0f), 1.0f);
+    } else {
+        r.cost = 0.0f;                                                           // fake_env.py:146
+    }
+    int rcol = c.D - 1;
+    if (c.predicts_cost) {                                                       // fake_env.py:139-142
+        r.cost = __fadd_rn(__fmul_rn(c.sig_out[rcol], raw(member, rcol)), c.mu_out[rcol]);
+        rcol -= 1;
+    }
+    r.rew = __fadd_rn(__fmul_rn(c.sig_out[rcol], raw(member, rcol)), c.mu_out[rcol]);   // :148-151
+    return r;
 }

@@ -72,10 +72,11 @@ int64_t cmbpo_ctx_launch_count(cmbpo_ctx* ctx);
 /*
  * Measurement hooks (bench.py's roofline): when enabled, CUDA events are recorded on the
  * context's stream around every launch of the dominant kernels.  slot 0 = the dynamics-ensemble
- * GEMM chain (K1), slot 1 = the GAE scan (K3).  _read synchronises, returns the summed device
+ * GEMM chain (K1), slot 1 = the GAE scan (K3), slot 2 = the rollout row kernel (K2), slot 3 = the
+ * policy pass (actor + V + VC chains + row kernel).  _read synchronises, returns the summed device
  * time and the number of bracketed launches, and optionally resets the slot.
  */
-enum { CMBPO_PROF_DYN = 0, CMBPO_PROF_GAE = 1, CMBPO_PROF_SLOTS = 2 };
+enum { CMBPO_PROF_DYN = 0, CMBPO_PROF_GAE = 1, CMBPO_PROF_STEP = 2, CMBPO_PROF_POLICY = 3, CMBPO_PROF_SLOTS = 4 };
 int cmbpo_ctx_profile(cmbpo_ctx* ctx, int enable);
 int cmbpo_ctx_profile_read(cmbpo_ctx* ctx, int slot, double* total_ms_host, int64_t* launches_host,
                            int reset);
