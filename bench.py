@@ -332,7 +332,9 @@ def run_cuda(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "fp16": "f16 (tcgen05 kind::f16, f32 accumulate)",
-                      "bf16": "bf16 (tcgen05 kind::f16, f32 accumulate)"}[args.precision],
+                      "bf16": "bf16 (tcgen05 kind::f16, f32 accumulate)",
+                      "fp16x2": "f16 (tcgen05 kind::f16, f32 accumulate, packed-f16 activations)",
+                      "bf16x2": "bf16 (tcgen05 kind::f16, f32 accumulate, packed-bf16 activations)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: HalfCheetahSafe H-step model rollout + GAE/cost-GAE + "
                                    "advantage normalisation",
@@ -377,7 +379,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16", "fp16x2", "bf16x2"])
     ap.add_argument("--batch", type=int, default=100000, help="start states per GPU")
     ap.add_argument("--cpu-batch", type=int, default=500, help="start states of the bounded CPU sample")
     args = ap.parse_args()

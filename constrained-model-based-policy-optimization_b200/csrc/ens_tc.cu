@@ -29,9 +29,12 @@ using namespace tc;
 
 namespace {
 
-constexpr int NTHREADS = 384;
-constexpr int STAGE = 8192;       // [64 neurons x 64 k x 2 B] weight tile
-constexpr int NS = 24;            // ring depth: 192 KB in flight
+constexpr int NTHREADS = 640;    // 4 control warps + 16 epilogue warps
+constexpr int TILE = 8192;        // [64 neurons x 64 k x 2 B] weight tile
+constexpr int STAGE = 4 * TILE;   // main-ring stage: up to 4 consecutive tiles (one mbarrier wait per 16 MMAs)
+constexpr int NSM = 5;            // main ring depth (160 KB)
+constexpr int W2SLOT = 24576;     // layer-2 ring slot: the W2 tiles of CPS consecutive chunks
+constexpr int NS2 = 2;
 constexpr int XA_BYTES = 16384;   // [128 rows x 64 k x 2 B]
 
 struct Stage {        // one weight tile image in the packed stream
@@ -40,22 +43,35 @@ struct Stage {        // one weight tile image in the packed stream
 };
 
 struct TcParams {
-    const uint8_t* wpack; unsigned long long member_bytes;
+    const uint8_t* wmain; unsigned long long main_bytes;   // per member: layer-0 + layer-1 tiles
+    const uint8_t* w2; unsigned long long w2_bytes;        // per member: layer-2 tiles
     const float* bias; int bias_stride;
-    int E, K0, KS0, Nout, NP, parts;             // parts = 2 when NP > 64 (layer-2 N split in halves)
+    int E, K0, KS0, Nout, NP, parts, cps;        // parts = 2 when NP > 64; cps = chunks per W2 slot
     const float* x; long long N; int ldx;
     const float *mu_in, *sig_in;
     float* out; long long out_member_stride;   // out[e*stride + row*Nout + c]
     int ntiles;
+    int act_x2;                // packed 16-bit activation math (precision modes *_X2)
+    int role_mode;             // experiment: 1 = control warps get the highest warp ids
     unsigned long long* dbg;   // optional [grid][16] cycle counters (protocol timing aid)
 };
 
 // barrier indices
-enum { W_FULL = 0, W_EMPTY = NS, D_FULL = 2 * NS, D_EMPTY = 2 * NS + 2, H1_FULL = 2 * NS + 4,
-       H2_FULL = 2 * NS + 5, H2_EMPTY = 2 * NS + 7, OUT_FULL = 2 * NS + 9, OUT_EMPTY = 2 * NS + 10,
-       X_FULL = 2 * NS + 11, NBAR = 2 * NS + 12 };
-constexpr int SMEM_BAR = XA_BYTES + NS * STAGE;
+enum { W_FULL = 0, W_EMPTY = NSM, W2_FULL = 2 * NSM, W2_EMPTY = 2 * NSM + NS2, D_FULL = 2 * NSM + 2 * NS2,
+       D_EMPTY = D_FULL + 2, H1_FULL = D_FULL + 4, H2_FULL = D_FULL + 5, H2_EMPTY = D_FULL + 7,
+       OUT_FULL = D_FULL + 9, OUT_EMPTY = D_FULL + 10, X_FULL = D_FULL + 11, NBAR = D_FULL + 12 };
+constexpr int SMEM_W2 = XA_BYTES + NSM * STAGE;
+constexpr int SMEM_BAR = SMEM_W2 + NS2 * W2SLOT;
 constexpr int SMEM_TOTAL = SMEM_BAR + NBAR * 8 + 16;
+
+// event trace of CTA 0, member 8 (steady state), kept in shared memory so that tracing does not
+// perturb the timeline; 3 streams (MMA warp, epilogue pair 0, pair 1) x 64 events of (tag, clock)
+#define TRACE(stream, tag)                                                                    \
+    if (DBG && p.dbg && blockIdx.x == 0 && m == 8 && lane == 0 && (warp & 3) == ((stream) == 0 ? 1 : 0)) { \
+        uint32_t* t_ = trace_smem + (stream) * 130;                                           \
+        uint32_t n_ = t_[0];                                                                  \
+        if (n_ < 64) { t_[2 + n_ * 2] = (tag); t_[3 + n_ * 2] = (uint32_t)clock64(); t_[0] = n_ + 1; } \
+    }
 
 template <bool DBG>
 __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc) {
@@ -74,12 +90,39 @@ template <int ACT> __device__ __forceinline__ float activate(float x) {
     return x;
 }
 
+// Packed 16-bit activation of two pre-activations: ONE MUFU op (tanh.approx.{f16x2,bf16x2}) and one
+// packed FMA for two elements, result already in the operand format of the next MMA.  Half the
+// MUFU / FMA-pipe load of the fp32 path at the price of one extra 16-bit rounding of the
+// pre-activation (opt-in precision modes *_X2).
+template <int FMT, int ACT>
+__device__ __forceinline__ uint32_t activate_x2(float x0, float x1) {
+    uint32_t t, th, r;
+    if (ACT == CMBPO_ACT_SWISH) { x0 *= 0.5f; x1 *= 0.5f; }
+    if (FMT == 0) {
+        x0 = fminf(fmaxf(x0, -30000.f), 30000.f);          // 2t must stay finite in fp16
+        x1 = fminf(fmaxf(x1, -30000.f), 30000.f);
+        __half2 h = __floats2half2_rn(x0, x1);
+        t = *reinterpret_cast<uint32_t*>(&h);
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(t));
+        if (ACT == CMBPO_ACT_TANH) return th;
+        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(t), "r"(th));
+    } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+        t = *reinterpret_cast<uint32_t*>(&h);
+        asm("tanh.approx.bf16x2 %0, %1;" : "=r"(th) : "r"(t));
+        if (ACT == CMBPO_ACT_TANH) return th;
+        asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(t), "r"(th));
+    }
+    return r;
+}
+
 // 32 accumulator columns of this thread's row -> +bias, act -> 16-bit pairs -> 16 TMEM columns.
 // The accumulator buffer is released (`d_empty`) as soon as the values sit in registers; the
 // destination is only waited for (`dst_free`, may be null) right before the store.
 template <int FMT, int ACT>
-__device__ __forceinline__ void drain32(uint32_t d_addr, const float* __restrict__ bias, uint32_t dst_addr,
-                                        uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity) {
+__device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32_t dst_addr,
+                                        uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity,
+                                        bool x2) {
     uint32_t r[32];
     tmem_ld32(d_addr, r);
     tmem_ld_wait();
@@ -87,10 +130,20 @@ __device__ __forceinline__ void drain32(uint32_t d_addr, const float* __restrict
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(d_empty);
     uint32_t q[16];
-    const float4* b4 = reinterpret_cast<const float4*>(bias);
+    // lane l holds bias[l] of this warp's 32 columns (one coalesced load issued BEFORE the accumulator
+    // wait; shared memory is carved to the limit so there is no L1 to serve per-thread bias loads)
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const float4 b = __ldg(b4 + c);
+        float4 b;
+        b.x = __shfl_sync(0xffffffffu, bias_lane, 4 * c + 0);
+        b.y = __shfl_sync(0xffffffffu, bias_lane, 4 * c + 1);
+        b.z = __shfl_sync(0xffffffffu, bias_lane, 4 * c + 2);
+        b.w = __shfl_sync(0xffffffffu, bias_lane, 4 * c + 3);
+        if (x2) {
+            q[2 * c] = activate_x2<FMT, ACT>(__uint_as_float(r[4 * c + 0]) + b.x, __uint_as_float(r[4 * c + 1]) + b.y);
+            q[2 * c + 1] = activate_x2<FMT, ACT>(__uint_as_float(r[4 * c + 2]) + b.z, __uint_as_float(r[4 * c + 3]) + b.w);
+            continue;
+        }
         const float v0 = activate<ACT>(__uint_as_float(r[4 * c + 0]) + b.x);
         const float v1 = activate<ACT>(__uint_as_float(r[4 * c + 1]) + b.y);
         const float v2 = activate<ACT>(__uint_as_float(r[4 * c + 2]) + b.z);
@@ -106,27 +159,39 @@ __device__ __forceinline__ void drain32(uint32_t d_addr, const float* __restrict
 
 template <int HD, int FMT, int ACT, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams p) {
-    constexpr int NC = HD / 64;        // 64-column chunks of a hidden layer
-    constexpr int KP = HD / 64;        // 64-wide K panels of layer 1
+    constexpr int NC = HD / 64;                     // 64-column chunks of a hidden layer
+    constexpr int KP = HD / 64;                     // 64-wide K panels of layer 1
+    constexpr int TPS = KP < 4 ? KP : 4;            // layer-1 tiles (K panels) per main-ring stage
+    constexpr int G0 = NC < 4 ? NC : 4;             // layer-0 chunk tiles per main-ring stage
     constexpr uint32_t COL_H1 = 0, COL_D = HD / 2, COL_H2 = COL_D + 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sXA = smem;
     uint8_t* sW = smem + XA_BYTES;
+    uint8_t* sW2 = smem + SMEM_W2;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + NBAR * 8);
+    uint32_t* trace_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + NBAR * 8 + 16);   // DBG only (1560 B)
+    if (DBG && threadIdx.x < 3) trace_smem[threadIdx.x * 130] = 0;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Warp ids: 0-15 epilogue, 16 = weight producer, 17 = MMA issuer, 18 = TMEM allocator, 19 = W2
+    // producer.  The SM's issue arbiter prefers the highest warp id, so the control warps (whose
+    // instructions gate everything else) are never starved by the 4 epilogue warps on their sub-core.
+    const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = p.role_mode ? (hw_warp + 4) % 20 : hw_warp;   // logical role id: 0-3 control, 4-19 epilogue
     const int nh2 = (p.parts == 1) ? 2 : 1;                    // H2 buffers (TMEM budget)
     const uint32_t col_out = 512u - (uint32_t)p.NP;            // OUT occupies the top NP columns
+    const int NPp = p.NP / p.parts;
+    const uint32_t w2_chunk_bytes = (uint32_t)p.NP * 128u;     // all parts of one chunk
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(bar + W_FULL + i, 1); mbar_init(bar + W_EMPTY + i, 1); }
+        for (int i = 0; i < NSM; ++i) { mbar_init(bar + W_FULL + i, 1); mbar_init(bar + W_EMPTY + i, 1); }
+        for (int i = 0; i < NS2; ++i) { mbar_init(bar + W2_FULL + i, 1); mbar_init(bar + W2_EMPTY + i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar + D_FULL + i, 1); mbar_init(bar + D_EMPTY + i, 8);
             mbar_init(bar + H2_FULL + i, 8); mbar_init(bar + H2_EMPTY + i, 1);
         }
         mbar_init(bar + H1_FULL, 8 * NC);
-        mbar_init(bar + OUT_FULL, 1); mbar_init(bar + OUT_EMPTY, 4);
+        mbar_init(bar + OUT_FULL, 1); mbar_init(bar + OUT_EMPTY, 16);
         mbar_init(bar + X_FULL, 4);
         fence_barrier_init();
     }
@@ -139,122 +204,164 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     // back from shared memory forces a per-instruction R2UR waterfall, ~100 cycles per MMA).
     if (*tmem_slot != 0u) { if (threadIdx.x == 0) printf("cmbpo: unexpected TMEM base %u\n", *tmem_slot); __trap(); }
     constexpr uint32_t tmem = 0u;
-    const uint32_t w2_bytes = (uint32_t)(p.NP / p.parts) * 128u;
-    // members are visited in a CTA-dependent rotation so that the 148 CTAs do not all stream the
-    // same weight tiles at the same time (spreads the L2 traffic over E x more addresses)
-    const int e_rot = blockIdx.x % p.E;
+    // Work unit = (row tile, member): the ntiles*E units are split into contiguous, equal ranges, one
+    // per CTA, so the last wave is balanced to within one member (a tile-granular split leaves the
+    // last of ceil(782/148) = 6 rounds 72% empty), and neighbouring CTAs start on different members,
+    // which spreads the weight streaming over E x more L2 addresses.
+    const long long n_units = (long long)p.ntiles * p.E;
+    const long long u0 = n_units * blockIdx.x / gridDim.x, u1 = n_units * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == 0) {
-        // ===== weight producer: streams the per-member stage program in consumption order =====
+        // ===== main weight producer: layer-0 and layer-1 tiles, 32 KB per stage =====
         uint32_t s = 0, ph = 0;
         unsigned long long c_wempty = 0;
         const long long t_begin = DBG ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            for (int ei = 0; ei < p.E; ++ei) {
-                const int e = (ei + e_rot) % p.E;
-                const uint8_t* src = p.wpack + (unsigned long long)e * p.member_bytes;
+        for (long long u = u0; u < u1; ++u) {
+            {
+                const int e = (int)(u % p.E);
+                const uint8_t* src = p.wmain + (unsigned long long)e * p.main_bytes;
                 auto push = [&](uint32_t bytes) {
                     wait_t<DBG>(bar + W_EMPTY + s, ph ^ 1, c_wempty);
                     if (elect_one()) {
                         mbar_expect_tx(bar + W_FULL + s, bytes);
                         bulk_g2s(sW + s * STAGE, src, bytes, bar + W_FULL + s);
                     }
+                    __syncwarp();
                     src += bytes;
-                    if (++s == NS) { s = 0; ph ^= 1; }
+                    if (++s == NSM) { s = 0; ph ^= 1; }
                 };
-                for (int j = 0; j < NC; ++j) push(STAGE);
-                for (int j = 0; j < NC; ++j) {
-                    for (int kp = 0; kp < KP; ++kp) push(STAGE);
-                    if (j >= 1) for (int q = 0; q < p.parts; ++q) push(w2_bytes);
-                }
-                for (int q = 0; q < p.parts; ++q) push(w2_bytes);
+                for (int j0 = 0; j0 < NC; j0 += G0) push(G0 * TILE);
+                for (int j = 0; j < NC; ++j)
+                    for (int kq = 0; kq < KP / TPS; ++kq) push(TPS * TILE);
             }
         }
         if (DBG && p.dbg && lane == 0) {
             p.dbg[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_begin);
             p.dbg[blockIdx.x * 16 + 1] = c_wempty;
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: warp-uniform control flow, lane 0 issues every tcgen05.mma / commit =====
-        const uint32_t idesc_h = idesc_f16(FMT, 64);
-        const uint32_t idesc_o = idesc_f16(FMT, p.NP / p.parts);
-        const uint64_t dXA = smem_desc_sw128(smem_u32(sXA));
-        const uint64_t dW0 = smem_desc_sw128(smem_u32(sW));
-        uint32_t s = 0, ph = 0, g = 0, m = 0, c1 = 0, it = 0;
-        unsigned long long c_w = 0, c_d = 0, c_h1 = 0, c_h2 = 0, c_out = 0, c_x = 0;
-        const long long t_begin = DBG ? clock64() : 0;
-        auto next_stage = [&]() { if (++s == NS) { s = 0; ph ^= 1; } };
-        auto l2_partial = [&](int jj) {             // OUT += H2[chunk jj] x W2[rows of chunk jj]
-            const uint32_t hb = (nh2 == 2) ? (c1 & 1) : 0, hn = (nh2 == 2) ? (c1 >> 1) : c1;
-            if (jj == 0) wait_t<DBG>(bar + OUT_EMPTY, (m & 1) ^ 1, c_out);
-            wait_t<DBG>(bar + H2_FULL + hb, hn & 1, c_h2);
-            for (int q = 0; q < p.parts; ++q) {
-                wait_t<DBG>(bar + W_FULL + s, ph, c_w);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t dB = dW0 + (uint64_t)(s * (STAGE >> 4));
-                    const uint32_t dcol = tmem + col_out + q * (p.NP / p.parts);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_f16_ts(dcol, tmem + COL_H2 + hb * 32 + ks * 8, dB + 2 * ks, idesc_o, !(jj == 0 && ks == 0));
-                    mma_commit(bar + W_EMPTY + s);
-                }
-                __syncwarp();
-                next_stage();
-            }
-            if (elect_one()) mma_commit(bar + H2_EMPTY + hb);
-            __syncwarp();
-            ++c1;
-        };
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            wait_t<DBG>(bar + X_FULL, it & 1, c_x);
-            tc_fence_after();
-            for (int ei = 0; ei < p.E; ++ei) {
-                for (int j = 0; j < NC; ++j) {              // layer 0: D = XA x W0 chunk
-                    const uint32_t buf = g & 1, n = g >> 1;
-                    wait_t<DBG>(bar + D_EMPTY + buf, (n & 1) ^ 1, c_d);
-                    wait_t<DBG>(bar + W_FULL + s, ph, c_w);
-                    tc_fence_after();
+    } else if (warp == 3) {
+        // ===== layer-2 weight producer: the W2 tiles of `cps` consecutive chunks per slot =====
+        uint32_t s2 = 0, ph2 = 0;
+        unsigned long long dummy = 0;
+        for (long long u = u0; u < u1; ++u) {
+            {
+                const int e = (int)(u % p.E);
+                const uint8_t* src = p.w2 + (unsigned long long)e * p.w2_bytes;
+                for (int j0 = 0; j0 < NC; j0 += p.cps) {
+                    const int nchunks = (NC - j0) < p.cps ? (NC - j0) : p.cps;
+                    const uint32_t bytes = (uint32_t)nchunks * w2_chunk_bytes;
+                    wait_t<false>(bar + W2_EMPTY + s2, ph2 ^ 1, dummy);
                     if (elect_one()) {
-                        const uint64_t dB = dW0 + (uint64_t)(s * (STAGE >> 4));
-                        for (int ks = 0; ks < p.KS0; ++ks)
-                            mma_f16(tmem + COL_D + buf * 64, dXA + 2 * ks, dB + 2 * ks, idesc_h, ks > 0);
-                        mma_commit(bar + W_EMPTY + s);
-                        mma_commit(bar + D_FULL + buf);
+                        mbar_expect_tx(bar + W2_FULL + s2, bytes);
+                        bulk_g2s(sW2 + s2 * W2SLOT, src, bytes, bar + W2_FULL + s2);
                     }
                     __syncwarp();
+                    src += bytes;
+                    if (++s2 == NS2) { s2 = 0; ph2 ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: warp-uniform control flow, one elected lane issues every tcgen05.mma / commit =====
+        const uint32_t idesc_h = idesc_f16(FMT, 64);
+        const uint32_t idesc_o = idesc_f16(FMT, NPp);
+        const uint64_t dXA = smem_desc_sw128(smem_u32(sXA));
+        const uint64_t dW0 = smem_desc_sw128(smem_u32(sW));
+        const uint64_t dW2 = smem_desc_sw128(smem_u32(sW2));
+        uint32_t s = 0, ph = 0, s2 = 0, ph2 = 0, g = 0, m = 0, c1 = 0, it = 0;
+        unsigned long long c_w = 0, c_d = 0, c_h1 = 0, c_h2 = 0, c_out = 0, c_x = 0;
+        const long long t_begin = DBG ? clock64() : 0;
+        auto next_stage = [&]() { if (++s == NSM) { s = 0; ph ^= 1; } };
+        auto l2_partial = [&](int jj) {             // OUT += H2[chunk jj] x W2[rows of chunk jj]
+            const uint32_t hb = (nh2 == 2) ? (c1 & 1) : 0, hn = (nh2 == 2) ? (c1 >> 1) : c1;
+            const int jin = jj % p.cps;
+            if (jin == 0) wait_t<DBG>(bar + W2_FULL + s2, ph2, c_w);
+            if (jj == 0) wait_t<DBG>(bar + OUT_EMPTY, (m & 1) ^ 1, c_out);
+            wait_t<DBG>(bar + H2_FULL + hb, hn & 1, c_h2);
+            tc_fence_after();
+            TRACE(0, 700 + jj);
+            const bool last_in_slot = (jin == p.cps - 1) || (jj == NC - 1);
+            if (elect_one()) {
+                for (int q = 0; q < p.parts; ++q) {
+                    const uint64_t dB = dW2 + (uint64_t)((s2 * W2SLOT + (jin * p.parts + q) * NPp * 128) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        mma_f16_ts(tmem + col_out + q * NPp, tmem + COL_H2 + hb * 32 + ks * 8, dB + 2 * ks, idesc_o,
+                                   !(jj == 0 && ks == 0));
+                }
+                mma_commit(bar + H2_EMPTY + hb);
+                if (last_in_slot) mma_commit(bar + W2_EMPTY + s2);
+            }
+            __syncwarp();
+            if (last_in_slot) { if (++s2 == NS2) { s2 = 0; ph2 ^= 1; } }
+            ++c1;
+        };
+        int cur_tile = -1;
+        for (long long u = u0; u < u1; ++u) {
+            const int tile = (int)(u / p.E);
+            if (tile != cur_tile) {                 // a new row tile: its XA panel must have landed
+                cur_tile = tile;
+                wait_t<DBG>(bar + X_FULL, it & 1, c_x);
+                tc_fence_after();
+                ++it;
+            }
+            {
+                for (int j0 = 0; j0 < NC; j0 += G0) {       // layer 0: D = XA x W0 chunk (G0 chunks per stage)
+                    wait_t<DBG>(bar + W_FULL + s, ph, c_w);
+#pragma unroll
+                    for (int jj = 0; jj < G0; ++jj) {
+                        const uint32_t buf = g & 1, n = g >> 1;
+                        wait_t<DBG>(bar + D_EMPTY + buf, (n & 1) ^ 1, c_d);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t dB = dW0 + (uint64_t)((s * STAGE + jj * TILE) >> 4);
+                            for (int ks = 0; ks < p.KS0; ++ks)
+                                mma_f16(tmem + COL_D + buf * 64, dXA + 2 * ks, dB + 2 * ks, idesc_h, ks > 0);
+                            mma_commit(bar + D_FULL + buf);
+                            if (jj == G0 - 1) mma_commit(bar + W_EMPTY + s);
+                        }
+                        __syncwarp();
+                        TRACE(0, 100 + j0 + jj);
+                        ++g;
+                    }
                     next_stage();
-                    ++g;
                 }
                 wait_t<DBG>(bar + H1_FULL, m & 1, c_h1);
                 tc_fence_after();
+                TRACE(0, 200);
                 for (int j = 0; j < NC; ++j) {              // layer 1 (+ layer 2 of the previous chunk)
                     const uint32_t buf = g & 1, n = g >> 1;
                     wait_t<DBG>(bar + D_EMPTY + buf, (n & 1) ^ 1, c_d);
                     tc_fence_after();
-#pragma unroll 2
-                    for (int kp = 0; kp < KP; ++kp) {
+                    TRACE(0, 300 + j);
+                    for (int kq = 0; kq < KP / TPS; ++kq) {
                         wait_t<DBG>(bar + W_FULL + s, ph, c_w);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t dB = dW0 + (uint64_t)(s * (STAGE >> 4));
-                            const uint32_t aT = tmem + COL_H1 + kp * 32;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                mma_f16_ts(tmem + COL_D + buf * 64, aT + ks * 8, dB + 2 * ks, idesc_h, (kp | ks) > 0);
+                            for (int tt = 0; tt < TPS; ++tt) {
+                                const uint64_t dB = dW0 + (uint64_t)((s * STAGE + tt * TILE) >> 4);
+                                const uint32_t aT = tmem + COL_H1 + (kq * TPS + tt) * 32;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    mma_f16_ts(tmem + COL_D + buf * 64, aT + ks * 8, dB + 2 * ks, idesc_h,
+                                               (kq | tt | ks) > 0);
+                            }
                             mma_commit(bar + W_EMPTY + s);
+                            if (kq == KP / TPS - 1) mma_commit(bar + D_FULL + buf);
                         }
                         __syncwarp();
                         next_stage();
                     }
-                    if (elect_one()) mma_commit(bar + D_FULL + buf);
-                    __syncwarp();
                     ++g;
+                    TRACE(0, 400 + j);
                     if (j >= 1) l2_partial(j - 1);
+                    TRACE(0, 500 + j);
                 }
                 l2_partial(NC - 1);
                 if (elect_one()) mma_commit(bar + OUT_FULL);
                 __syncwarp();
+                TRACE(0, 600);
                 ++m;
             }
         }
@@ -264,17 +371,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             d[3] = c_w; d[4] = c_d; d[5] = c_h1; d[6] = c_h2; d[7] = c_out; d[8] = c_x;
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 2 warpgroups x 128 threads, thread <-> row =====
+        // ===== epilogue: 4 warpgroups; pair (wg>>1) owns accumulator buffer (wg>>1), half (wg&1) its columns =====
         const int wg = (warp - 4) >> 2;
-        const int wq = warp & 3;                   // TMEM lane quarter this warp may access
+        const uint32_t pair = (uint32_t)wg >> 1, half = (uint32_t)wg & 1;
+        const int wq = hw_warp & 3;                // TMEM lane quarter this warp may access
         const int row = wq * 32 + lane;
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
         uint32_t g = 0, m = 0, c1 = 0;
         unsigned long long c_dfull = 0, c_drain = 0, c_outw = 0;
         const long long t_begin = DBG ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const long long grow = (long long)tile * 128 + row;
-            if (wg == 0) {
+        // deferred OUT epilogue: the four warpgroups split the NP output columns (16 or 32 each)
+        int prev_e = 0; long long prev_grow = 0; uint32_t prev_m = 0; bool have_prev = false;
+        const int out_cw = (p.NP <= 64) ? 16 : 32;
+        auto out_epilogue = [&]() {
+            wait_t<DBG>(bar + OUT_FULL, prev_m & 1, c_outw);
+            tc_fence_after();
+            const int c_begin = wg * out_cw;
+            uint32_t r[32];
+            const bool mine = c_begin < p.NP;
+            if (mine) {
+                tmem_ld16(tmem + col_out + c_begin + lane_base, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+                if (out_cw == 32) tmem_ld16(tmem + col_out + c_begin + 16 + lane_base, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar + OUT_EMPTY);          // accumulator free again (16 warps arrive)
+            if (mine && prev_grow < p.N) {
+                float* orow = p.out + (long long)prev_e * p.out_member_stride + prev_grow * p.Nout;
+                const float* b2 = p.bias + (long long)prev_e * p.bias_stride + 2 * HD;
+                if ((p.Nout & 3) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const int c = c_begin + i;
+                        if (i < out_cw && c < p.Nout) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + c));
+                            float4 v;
+                            v.x = __uint_as_float(r[i]) + b.x; v.y = __uint_as_float(r[i + 1]) + b.y;
+                            v.z = __uint_as_float(r[i + 2]) + b.z; v.w = __uint_as_float(r[i + 3]) + b.w;
+                            *reinterpret_cast<float4*>(orow + c) = v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int c = c_begin + i;
+                        if (i < out_cw && c < p.Nout) orow[c] = __uint_as_float(r[i]) + b2[c];
+                    }
+                }
+            }
+            have_prev = false;
+        };
+        int cur_tile = -1;
+        long long grow = 0;
+        for (long long u = u0; u < u1; ++u) {
+            const int tile = (int)(u / p.E);
+            const bool new_tile = tile != cur_tile;
+            cur_tile = tile;
+            grow = (long long)tile * 128 + row;
+            if (new_tile && wg == 0) {
                 // XA: this row of the input, scaled (pens/utils.py:156), 16-bit, zero padded to 64
                 const float* xr = p.x + grow * p.ldx;
 #pragma unroll
@@ -299,57 +454,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar + X_FULL);
             }
-            for (int ei = 0; ei < p.E; ++ei) {
-                const int e = (ei + e_rot) % p.E;
+            {
+                const int e = (int)(u % p.E);
                 const float* bias = p.bias + (long long)e * p.bias_stride;
-                for (int j = 0; j < NC; ++j) {                  // layer-0 chunk -> H1 columns
-                    const uint32_t buf = g & 1, n = g >> 1;
+                // Each pair drains every other chunk (chunk j <-> accumulator buffer j&1 <-> pair), so the
+                // loops below run over this pair's chunks only.  The bias of the NEXT drain (lane l holds
+                // bias[l] of this warp's 32 columns) is loaded one drain ahead: its latency hides behind
+                // the current drain / the accumulator wait, and the loops stay rolled (the fully unrolled
+                // variant overflowed the instruction cache and doubled the drain time).
+                float bias_next = __ldg(bias + pair * 64 + half * 32 + lane);
+                for (int i = 0; i < NC / 2; ++i) {               // layer-0 chunk j -> H1 columns
+                    const int j = 2 * i + (int)pair;
+                    const uint32_t gg = g + j, buf = pair, n = gg >> 1;
+                    const float bias_lane = bias_next;
+                    bias_next = (i + 1 < NC / 2) ? __ldg(bias + (j + 2) * 64 + half * 32 + lane)
+                                                 : __ldg(bias + HD + pair * 64 + half * 32 + lane);
                     wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
                     tc_fence_after();
+                    if (half == 0) { TRACE(1 + pair, 1000 + j); }
                     const long long td = DBG ? clock64() : 0;
-                    drain32<FMT, ACT>(tmem + COL_D + buf * 64 + wg * 32 + lane_base, bias + j * 64 + wg * 32,
-                                      tmem + COL_H1 + j * 32 + wg * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0);
+                    drain32<FMT, ACT>(tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
+                                      tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0, p.act_x2 != 0);
                     if (DBG) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar + H1_FULL);
-                    ++g;
+                    if (half == 0) { TRACE(1 + pair, 1100 + j); }
                 }
-                for (int j = 0; j < NC; ++j) {                  // layer-1 chunk -> an H2 buffer
-                    const uint32_t buf = g & 1, n = g >> 1;
-                    const uint32_t hb = (nh2 == 2) ? (c1 & 1) : 0, hn = (nh2 == 2) ? (c1 >> 1) : c1;
+                g += NC;
+                // The previous member's OUT accumulator is drained HERE, after this member's layer-0
+                // drains: the accumulator is not touched again before this member's first layer-2
+                // MMA, so the global stores stay off the MMA warp's critical path.
+                if (have_prev) out_epilogue();
+                for (int i = 0; i < NC / 2; ++i) {               // layer-1 chunk j -> an H2 buffer
+                    const int j = 2 * i + (int)pair;
+                    const uint32_t gg = g + j, buf = pair, n = gg >> 1, cc = c1 + j;
+                    const uint32_t hb = (nh2 == 2) ? (cc & 1) : 0, hn = (nh2 == 2) ? (cc >> 1) : cc;
+                    const float bias_lane = bias_next;
+                    if (i + 1 < NC / 2) bias_next = __ldg(bias + HD + (j + 2) * 64 + half * 32 + lane);
                     wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
                     tc_fence_after();
+                    if (half == 0) { TRACE(1 + pair, 2000 + j); }
                     const long long td = DBG ? clock64() : 0;
-                    drain32<FMT, ACT>(tmem + COL_D + buf * 64 + wg * 32 + lane_base, bias + HD + j * 64 + wg * 32,
-                                      tmem + COL_H2 + hb * 32 + wg * 16 + lane_base, bar + D_EMPTY + buf,
-                                      bar + H2_EMPTY + hb, (hn & 1) ^ 1);
+                    drain32<FMT, ACT>(tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
+                                      tmem + COL_H2 + hb * 32 + half * 16 + lane_base, bar + D_EMPTY + buf,
+                                      bar + H2_EMPTY + hb, (hn & 1) ^ 1, p.act_x2 != 0);
                     if (DBG) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar + H2_FULL + hb);
-                    ++g; ++c1;
+                    if (half == 0) { TRACE(1 + pair, 2100 + j); }
                 }
-                if (wg == (int)(m & 1)) {                        // OUT -> global raw outputs (warpgroups alternate)
-                    wait_t<DBG>(bar + OUT_FULL, m & 1, c_outw);
-                    tc_fence_after();
-                    float* orow = p.out + (long long)e * p.out_member_stride + grow * p.Nout;
-                    const float* b2 = bias + 2 * HD;
-                    for (int c0 = 0; c0 < p.NP; c0 += 16) {
-                        uint32_t r[16];
-                        tmem_ld16(tmem + col_out + c0 + lane_base, r);
-                        tmem_ld_wait();
-                        if (grow < p.N) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (c0 + i < p.Nout) orow[c0 + i] = __uint_as_float(r[i]) + b2[c0 + i];
-                        }
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar + OUT_EMPTY);
-                }
+                g += NC; c1 += NC;
+                prev_e = e; prev_grow = grow; prev_m = m; have_prev = true;
                 ++m;
             }
         }
+        if (have_prev) out_epilogue();
         if (DBG && p.dbg && warp == 4 && lane == 0) {
             unsigned long long* d = p.dbg + blockIdx.x * 16;
             d[9] = (unsigned long long)(clock64() - t_begin);
@@ -358,6 +517,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     }
     tc_fence_before();
     __syncthreads();
+    if (DBG && p.dbg && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 390; i += NTHREADS) p.dbg[4096 + i] = trace_smem[i];
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
@@ -405,32 +566,39 @@ OutShape out_shape(int Nout) {
     return {((Nout + 31) / 32) * 32, 2};       // two N-halves, each a multiple of 16
 }
 
-// the order in which the MMA warp consumes weight tiles (must match the kernel's loops)
-std::vector<Stage> stage_program(int HD, int NP, int parts, unsigned long long* total) {
+// the order in which the MMA warp consumes weight tiles (must match the kernel's loops):
+// main stream = layer-0 chunk tiles, then per chunk the layer-1 K-panel tiles; W2 stream = per chunk
+// the layer-2 tile(s)
+void stage_programs(int HD, int NP, int parts, std::vector<Stage>* main_prog, unsigned long long* main_bytes,
+                    std::vector<Stage>* w2_prog, unsigned long long* w2_bytes) {
     const int NC = HD / 64, KP = HD / 64, NPp = NP / parts;
-    std::vector<Stage> v;
     unsigned long long off = 0;
-    auto add = [&](int layer, int n0, int k0, int rows) {
-        v.push_back(Stage{layer, n0, k0, rows, off});
-        off += (unsigned long long)rows * 128;
-    };
-    auto add_w2 = [&](int chunk) { for (int q = 0; q < parts; ++q) add(2, q * NPp, chunk * 64, NPp); };
-    for (int j = 0; j < NC; ++j) add(0, j * 64, 0, 64);
-    for (int j = 0; j < NC; ++j) {
-        for (int kp = 0; kp < KP; ++kp) add(1, j * 64, kp * 64, 64);
-        if (j >= 1) add_w2(j - 1);
-    }
-    add_w2(NC - 1);
-    *total = off;
-    return v;
+    for (int j = 0; j < NC; ++j) { main_prog->push_back(Stage{0, j * 64, 0, 64, off}); off += TILE; }
+    for (int j = 0; j < NC; ++j)
+        for (int kp = 0; kp < KP; ++kp) { main_prog->push_back(Stage{1, j * 64, kp * 64, 64, off}); off += TILE; }
+    *main_bytes = off;
+    off = 0;
+    for (int j = 0; j < NC; ++j)
+        for (int q = 0; q < parts; ++q) { w2_prog->push_back(Stage{2, q * NPp, j * 64, NPp, off}); off += (unsigned long long)NPp * 128; }
+    *w2_bytes = off;
+}
+
+int chunks_per_w2_slot(int HD, int NP) {
+    int cps = W2SLOT / (NP * 128);
+    int p2 = 1;
+    while (p2 * 2 <= cps) p2 *= 2;
+    const int NC = HD / 64;
+    return p2 < NC ? p2 : NC;
 }
 
 template <int HD, int FMT, int ACT, bool DBG>
 int launch_tc(cmbpo_ctx* ctx, const TcParams& p) {
-    const int smem = SMEM_TOTAL + 1024;
+    const int smem = SMEM_TOTAL + 1024 + (DBG ? 1568 : 0);
+    static_assert(SMEM_TOTAL + 1024 + 1568 <= 232448, "shared memory budget");
     auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT, DBG>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = p.ntiles < ctx->sm_count ? p.ntiles : ctx->sm_count;
+    const long long units = (long long)p.ntiles * p.E;
+    const int grid = units < ctx->sm_count ? (int)units : ctx->sm_count;
     kern<<<grid, NTHREADS, smem, ctx->stream>>>(p);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -461,45 +629,59 @@ bool ens_tc_supported(const Net& n) {
     return n.acts[0] == CMBPO_ACT_SWISH || n.acts[0] == CMBPO_ACT_TANH;
 }
 
-// pack both 16-bit formats once per weight upload
+// pack both 16-bit formats once per weight upload: [main stream | W2 stream] per precision
 int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
     const int HD = net.dims[1], K0 = net.dims[0], Nout = net.dims[3];
     const OutShape os = out_shape(Nout);
-    unsigned long long member_bytes = 0;
-    std::vector<Stage> prog = stage_program(HD, os.NP, os.parts, &member_bytes);
-    Stage* d_prog;
-    CUDA_TRY(cudaMalloc(&d_prog, prog.size() * sizeof(Stage)));
-    CUDA_TRY(cudaMemcpyAsync(d_prog, prog.data(), prog.size() * sizeof(Stage), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long main_bytes = 0, w2_bytes = 0;
+    std::vector<Stage> mp, wp;
+    stage_programs(HD, os.NP, os.parts, &mp, &main_bytes, &wp, &w2_bytes);
+    Stage *d_mp, *d_wp;
+    CUDA_TRY(cudaMalloc(&d_mp, mp.size() * sizeof(Stage)));
+    CUDA_TRY(cudaMalloc(&d_wp, wp.size() * sizeof(Stage)));
+    CUDA_TRY(cudaMemcpyAsync(d_mp, mp.data(), mp.size() * sizeof(Stage), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_wp, wp.data(), wp.size() * sizeof(Stage), cudaMemcpyHostToDevice, ctx->stream));
     for (int prec = CMBPO_PREC_BF16; prec <= CMBPO_PREC_FP16; ++prec) {
-        CUDA_TRY(cudaMalloc(&net.tc_pack[prec], (size_t)net.E * member_bytes));
-        net.tc_pack_bytes[prec] = (size_t)member_bytes;
-        dim3 grid((unsigned)prog.size(), net.E);
-        if (prec == CMBPO_PREC_FP16)
-            pack_weights_kernel<0><<<grid, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_prog,
-                                                               (int)prog.size(), member_bytes, (uint8_t*)net.tc_pack[prec]);
-        else
-            pack_weights_kernel<1><<<grid, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_prog,
-                                                               (int)prog.size(), member_bytes, (uint8_t*)net.tc_pack[prec]);
+        const size_t total = (size_t)net.E * (main_bytes + w2_bytes);
+        CUDA_TRY(cudaMalloc(&net.tc_pack[prec], total));
+        net.tc_pack_bytes[prec] = (size_t)main_bytes;       // W2 stream starts at E * main_bytes
+        uint8_t* base = (uint8_t*)net.tc_pack[prec];
+        uint8_t* base2 = base + (size_t)net.E * main_bytes;
+        dim3 g1((unsigned)mp.size(), net.E), g2((unsigned)wp.size(), net.E);
+        if (prec == CMBPO_PREC_FP16) {
+            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_mp, (int)mp.size(), main_bytes, base);
+            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_wp, (int)wp.size(), w2_bytes, base2);
+        } else {
+            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_mp, (int)mp.size(), main_bytes, base);
+            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_wp, (int)wp.size(), w2_bytes, base2);
+        }
     }
     CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)net.E * (2 * HD + os.NP) * sizeof(float)));
     pack_bias_kernel<<<net.E, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, Nout, os.NP, net.tc_bias);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(cudaFree(d_prog));
+    CUDA_TRY(cudaFree(d_mp));
+    CUDA_TRY(cudaFree(d_wp));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* out_raw, int precision) {
+    const int act_x2 = (precision == CMBPO_PREC_FP16_X2 || precision == CMBPO_PREC_BF16_X2) ? 1 : 0;
+    if (precision == CMBPO_PREC_FP16_X2) precision = CMBPO_PREC_FP16;
+    if (precision == CMBPO_PREC_BF16_X2) precision = CMBPO_PREC_BF16;
     CMBPO_CHECK(precision == CMBPO_PREC_BF16 || precision == CMBPO_PREC_FP16, "bad precision %d", precision);
     CMBPO_CHECK(net.tc_pack[precision], "tcgen05 weights not packed");
     if (N <= 0) return 0;
     const int HD = net.dims[1];
     const OutShape os = out_shape(net.dims[3]);
     TcParams p;
-    p.wpack = (const uint8_t*)net.tc_pack[precision];
-    p.member_bytes = net.tc_pack_bytes[precision];
     p.Nout = net.dims[3];
     p.NP = os.NP; p.parts = os.parts;
+    p.cps = chunks_per_w2_slot(HD, os.NP);
+    p.wmain = (const uint8_t*)net.tc_pack[precision];
+    p.main_bytes = net.tc_pack_bytes[precision];
+    p.w2 = p.wmain + (size_t)net.E * p.main_bytes;
+    p.w2_bytes = (unsigned long long)(HD / 64) * p.NP * 128;
     p.bias = net.tc_bias; p.bias_stride = 2 * HD + p.NP;
     p.E = net.E; p.K0 = net.dims[0]; p.KS0 = (p.K0 + 15) / 16;
     p.x = x; p.N = N; p.ldx = net.dims[0];
@@ -507,15 +689,18 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     p.out = out_raw; p.out_member_stride = (long long)N * p.Nout;
     p.ntiles = (int)((N + 127) / 128);
     p.dbg = nullptr;
+    p.act_x2 = act_x2;
+    { static const char* rm = getenv("CMBPO_TC_ROLES"); p.role_mode = rm ? atoi(rm) : 0; }
     static const char* dbg_env = getenv("CMBPO_TC_DEBUG");
     if (dbg_env && HD == 512 && net.acts[0] == CMBPO_ACT_SWISH && precision == CMBPO_PREC_FP16) {
         // protocol timing: per-CTA cycle counters printed once per launch (debug aid, off by default)
         unsigned long long* d;
-        if (cmbpo_ws_get(ctx, 1, (size_t)ctx->sm_count * 16 * 8, (void**)&d)) return 1;
-        CUDA_TRY(cudaMemsetAsync(d, 0, (size_t)ctx->sm_count * 16 * 8, ctx->stream));
+        const size_t dbg_words = 4096 + 3 * 1024;
+        if (cmbpo_ws_get(ctx, 1, dbg_words * 8, (void**)&d)) return 1;
+        CUDA_TRY(cudaMemsetAsync(d, 0, dbg_words * 8, ctx->stream));
         p.dbg = d;
         if (launch_tc<512, 0, CMBPO_ACT_SWISH, true>(ctx, p)) return 1;
-        std::vector<unsigned long long> h((size_t)ctx->sm_count * 16);
+        std::vector<unsigned long long> h(dbg_words);
         CUDA_TRY(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         const char* names[14] = {"prod_total", "prod_wait_wempty", "mma_total", "mma_wait_wfull", "mma_wait_dempty",
@@ -525,6 +710,17 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
             double sum = 0; int n = 0;
             for (int b = 0; b < ctx->sm_count && b < p.ntiles; ++b) { sum += (double)h[(size_t)b * 16 + k]; ++n; }
             fprintf(stderr, "tcdbg %-18s %12.0f cycles/CTA\n", names[k], sum / (n ? n : 1));
+        }
+        static int printed = 0;
+        if (!printed++) {
+            for (int st = 0; st < 3; ++st) {
+                const unsigned long long* t = h.data() + 4096 + st * 130;
+                uint32_t t0 = (uint32_t)h[4096 + 3];     // first MMA event
+                fprintf(stderr, "trace stream %d (%s):", st, st == 0 ? "mma" : (st == 1 ? "epi pair0" : "epi pair1"));
+                for (unsigned long long i = 0; i < t[0] && i < 64; ++i)
+                    fprintf(stderr, " %llu@%d", t[2 + i * 2], (int)((uint32_t)t[3 + i * 2] - t0));
+                fprintf(stderr, "\n");
+            }
         }
         return 0;
     }
