@@ -52,7 +52,7 @@ extern "C" int cmbpo_ctx_create(int device, cmbpo_ctx** out) {
     return 0;
 }
 
-static void free_net(Net& n) {
+void net_free(Net& n) {
     for (int l = 0; l < CMBPO_MAX_LAYERS; ++l) {
         if (n.W[l]) cudaFree(n.W[l]);
         if (n.b[l]) cudaFree(n.b[l]);
@@ -68,7 +68,8 @@ extern "C" int cmbpo_ctx_destroy(cmbpo_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (Net& n : ctx->nets) free_net(n);
+    for (Net& n : ctx->nets) net_free(n);
+    net_free(ctx->polnet);
     if (ctx->log_std) cudaFree(ctx->log_std);
     for (Workspace& w : ctx->ws) if (w.ptr) cudaFree(w.ptr);
     delete ctx;
@@ -128,8 +129,6 @@ static int upload(cmbpo_ctx* ctx, const float* src, size_t n, bool on_device, fl
     return 0;
 }
 
-int ens_tc_prepare(cmbpo_ctx* ctx, Net& net);
-
 extern "C" int cmbpo_net_set_weights(cmbpo_ctx* ctx, int which, int E, int n_layers, const int* dims,
                                      const float* const* W, const float* const* b, const int* acts,
                                      const float* mu_in, const float* var_in, const float* mu_out,
@@ -142,7 +141,7 @@ extern "C" int cmbpo_net_set_weights(cmbpo_ctx* ctx, int which, int E, int n_lay
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     Net& n = ctx->nets[which];
-    free_net(n);
+    net_free(n);
     n.E = E; n.n_layers = n_layers; n.probabilistic = probabilistic != 0;
     for (int l = 0; l <= n_layers; ++l) n.dims[l] = dims[l];
     const int last = dims[n_layers];
@@ -184,6 +183,7 @@ extern "C" int cmbpo_net_set_weights(cmbpo_ctx* ctx, int which, int E, int n_lay
     }
     n.loaded = true;
     if (ens_tc_supported(n) && ens_tc_prepare(ctx, n)) return 1;
+    if (which != CMBPO_NET_DYN && policy_pack_build(ctx)) return 1;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -53,6 +53,8 @@ struct Net {
     void* tc_pack[3] = {nullptr, nullptr, nullptr};   // per precision (index = CMBPO_PREC_*)
     size_t tc_pack_bytes[3] = {0, 0, 0};
     float* tc_bias = nullptr;   // biases re-laid for the epilogue
+    // merged nets only: hidden activation per member (CMBPO_ACT_*); all -1 for an ordinary ensemble
+    int member_act[CMBPO_MAX_E] = {-1, -1, -1, -1, -1, -1, -1, -1};
 };
 
 struct Workspace {
@@ -72,6 +74,11 @@ struct cmbpo_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     Net nets[CMBPO_NET_COUNT];
+    // actor + V + VC merged into ONE ensemble sharing one input panel (tcgen05 path only): member 0 =
+    // actor, then the V members, then the VC members; each member's own input scaler is folded into
+    // its first layer relative to the common transform (policy_pack.cu)
+    Net polnet;
+    int pol_nv = 0, pol_nvc = 0;
     float* log_std = nullptr;   // [A]
     int A = 0;
     Workspace ws[8];            // reusable scratch slots
@@ -112,5 +119,8 @@ int ens_forward_f32(cmbpo_ctx* ctx, const Net& net, const float* x, int64_t N, b
 int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* out_raw,
                    int precision);
 bool ens_tc_supported(const Net& net);
+int ens_tc_prepare(cmbpo_ctx* ctx, Net& net);
+int policy_pack_build(cmbpo_ctx* ctx);
+void net_free(Net& n);
 int ens_forward(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, bool x_is_3d, float* out_raw,
                 int precision);

@@ -53,6 +53,7 @@ struct TcParams {
     int ntiles;
     int act_x2;                // packed 16-bit activation math (precision modes *_X2)
     int role_mode;             // experiment: 1 = control warps get the highest warp ids
+    int member_act[CMBPO_MAX_E];   // ACT == 0 kernels (merged nets): hidden activation per member
     unsigned long long* dbg;   // optional [grid][16] cycle counters (protocol timing aid)
 };
 
@@ -155,6 +156,19 @@ __device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32
     tmem_st16(dst_addr, q);
     tmem_st_wait();
     tc_fence_before();
+}
+
+// ACT == 0: the activation is a per-member runtime value (merged policy ensemble)
+template <int FMT, int ACT>
+__device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, float bias_lane, uint32_t dst_addr,
+                                            uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity, bool x2) {
+    if (ACT != 0) {
+        drain32<FMT, ACT>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2);
+    } else if (act_rt == CMBPO_ACT_TANH) {
+        drain32<FMT, CMBPO_ACT_TANH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2);
+    } else {
+        drain32<FMT, CMBPO_ACT_SWISH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2);
+    }
 }
 
 template <int HD, int FMT, int ACT, bool DBG>
@@ -457,6 +471,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             {
                 const int e = (int)(u % p.E);
                 const float* bias = p.bias + (long long)e * p.bias_stride;
+                const int act_e = (ACT == 0) ? p.member_act[e] : ACT;
                 // Each pair drains every other chunk (chunk j <-> accumulator buffer j&1 <-> pair), so the
                 // loops below run over this pair's chunks only.  The bias of the NEXT drain (lane l holds
                 // bias[l] of this warp's 32 columns) is loaded one drain ahead: its latency hides behind
@@ -473,7 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     tc_fence_after();
                     if (half == 0) { TRACE(1 + pair, 1000 + j); }
                     const long long td = DBG ? clock64() : 0;
-                    drain32<FMT, ACT>(tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
+                    drain32_act<FMT, ACT>(act_e, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
                                       tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0, p.act_x2 != 0);
                     if (DBG) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
@@ -495,7 +510,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     tc_fence_after();
                     if (half == 0) { TRACE(1 + pair, 2000 + j); }
                     const long long td = DBG ? clock64() : 0;
-                    drain32<FMT, ACT>(tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
+                    drain32_act<FMT, ACT>(act_e, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
                                       tmem + COL_H2 + hb * 32 + half * 16 + lane_base, bar + D_EMPTY + buf,
                                       bar + H2_EMPTY + hb, (hn & 1) ^ 1, p.act_x2 != 0);
                     if (DBG) c_drain += (unsigned long long)(clock64() - td);
@@ -607,6 +622,7 @@ int launch_tc(cmbpo_ctx* ctx, const TcParams& p) {
 
 template <int HD, int FMT>
 int launch_tc_act(cmbpo_ctx* ctx, const TcParams& p, int act) {
+    if (act == 0) return launch_tc<HD, FMT, 0, false>(ctx, p);
     if (act == CMBPO_ACT_SWISH) return launch_tc<HD, FMT, CMBPO_ACT_SWISH, false>(ctx, p);
     return launch_tc<HD, FMT, CMBPO_ACT_TANH, false>(ctx, p);
 }
@@ -615,7 +631,8 @@ template <int FMT>
 int launch_tc_hd(cmbpo_ctx* ctx, const TcParams& p, int hd, int act) {
     if (hd == 128) return launch_tc_act<128, FMT>(ctx, p, act);
     if (hd == 256) return launch_tc_act<256, FMT>(ctx, p, act);
-    return launch_tc_act<512, FMT>(ctx, p, act);
+    if (act == CMBPO_ACT_SWISH) return launch_tc<512, FMT, CMBPO_ACT_SWISH, false>(ctx, p);
+    return launch_tc<512, FMT, CMBPO_ACT_TANH, false>(ctx, p);
 }
 
 }  // namespace
@@ -690,6 +707,8 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     p.ntiles = (int)((N + 127) / 128);
     p.dbg = nullptr;
     p.act_x2 = act_x2;
+    for (int i = 0; i < CMBPO_MAX_E; ++i) p.member_act[i] = net.member_act[i];
+    const int act_sel = net.member_act[0] >= 0 ? 0 : net.acts[0];
     { static const char* rm = getenv("CMBPO_TC_ROLES"); p.role_mode = rm ? atoi(rm) : 0; }
     static const char* dbg_env = getenv("CMBPO_TC_DEBUG");
     if (dbg_env && HD == 512 && net.acts[0] == CMBPO_ACT_SWISH && precision == CMBPO_PREC_FP16) {
@@ -724,6 +743,6 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
         }
         return 0;
     }
-    if (precision == CMBPO_PREC_FP16) return launch_tc_hd<0>(ctx, p, HD, net.acts[0]);
-    return launch_tc_hd<1>(ctx, p, HD, net.acts[0]);
+    if (precision == CMBPO_PREC_FP16) return launch_tc_hd<0>(ctx, p, HD, act_sel);
+    return launch_tc_hd<1>(ctx, p, HD, act_sel);
 }

@@ -14,8 +14,8 @@
 namespace {
 
 struct ValueHead {            // one non-probabilistic value ensemble read through PE.predict
-    const float* raw;         // [E, N, 1]
-    int E;
+    const float* raw;         // [E, N, ld], value in column 0
+    int E, ld;
     const float *mu_out, *sig_out;   // [1] or null
 };
 
@@ -23,7 +23,7 @@ __device__ __forceinline__ float value_of(const ValueHead& h, int64_t N, int64_t
     // tf.reduce_mean over members of inverse_transform(out) (pe.py:343, pens/utils.py:167)
     float s = 0.f;
     for (int e = 0; e < h.E; ++e) {
-        float m = h.raw[(int64_t)e * N + p];
+        float m = h.raw[((int64_t)e * N + p) * h.ld];
         if (h.mu_out) m = __fadd_rn(__fmul_rn(h.sig_out[0], m), h.mu_out[0]);
         s = (e == 0) ? m : __fadd_rn(s, m);
     }
@@ -83,9 +83,10 @@ __global__ void policy_rows_kernel(PolicyRowsArgs a) {
     if (a.xin) for (int o = 0; o < a.O; ++o) a.xin[p * (a.O + a.A) + o] = a.obs[p * a.O + o];
 }
 
-struct RawDyn {
-    const float* raw; int64_t N; int W; int64_t p;
-    __device__ float operator()(int e, int c) const { return raw[((int64_t)e * N + p) * W + c]; }
+struct RawDyn {             // raw outputs [E, N, W]: row pointer of member 0 + member stride
+    const float* row0; int64_t estride;
+    __device__ RawDyn(const float* raw, int64_t N, int W, int64_t p) : row0(raw + p * W), estride(N * (int64_t)W) {}
+    __device__ float operator()(int e, int c) const { return __ldg(row0 + (int64_t)e * estride + c); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -113,7 +114,7 @@ struct EnvStepArgs {
     double* dkl_sum;   // 1 double accumulator
 };
 
-__global__ void __launch_bounds__(ROW_THREADS) env_step_kernel(EnvStepArgs a) {
+__global__ void __launch_bounds__(ROW_THREADS, 4) env_step_kernel(EnvStepArgs a) {
     __shared__ RowShared sh;
     const int O = a.O, RB = ROW_THREADS / O;
     const int rb = threadIdx.x / O, dim = threadIdx.x - rb * O;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(ROW_THREADS) env_step_kernel(EnvStepArgs a) {
             const int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, gid, a.step, a.n_elite);
             member = a.c.elite[pos];
             const float eps = (!a.c.deterministic && a.state_eps) ? a.state_eps[p * O + dim] : 1.0f;
-            RawDyn raw{a.raw, a.N, 2 * a.c.D, p};
+            RawDyn raw(a.raw, a.N, 2 * a.c.D, p);
             EnvDimOut d = env_dim(a.c, raw, dim, member, a.obs[p * O + dim], eps);
             sh.kl[threadIdx.x] = d.kl; sh.epv[threadIdx.x] = d.epv; sh.nx[threadIdx.x] = d.nx;
             sh.fin[threadIdx.x] = isfinite(d.nx) ? 1 : 0;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(ROW_THREADS) env_step_kernel(EnvStepArgs a) {
         }
         __syncthreads();
         if (active && dim == 0) {
-            RawDyn raw{a.raw, a.N, 2 * a.c.D, p};
+            RawDyn raw(a.raw, a.N, 2 * a.c.D, p);
             EnvRowOut r = env_row_finish(a.c, raw, member, sh.kl + rb * O, sh.epv + rb * O, sh.nx + rb * O,
                                          sh.fin + rb * O);
             a.rew[p] = r.rew; a.cost[p] = r.cost; a.term[p] = r.term ? 1 : 0;
@@ -169,7 +170,7 @@ struct StepArgs {
     cmbpo_rollout_bufs b;
 };
 
-__global__ void __launch_bounds__(ROW_THREADS) rollout_step_kernel(StepArgs a) {
+__global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a) {
     __shared__ RowShared sh;
     const int O = a.O, A = a.A, t = a.t, RB = ROW_THREADS / O;
     const int rb = threadIdx.x / O, dim = threadIdx.x - rb * O;
@@ -188,14 +189,14 @@ __global__ void __launch_bounds__(ROW_THREADS) rollout_step_kernel(StepArgs a) {
             if (!a.c.deterministic)
                 eps = a.state_eps ? a.state_eps[p * O + dim] : philox_normal(a.seed, gid, t, RNG_STREAM_STATE, dim);
             obs_d = a.cur_obs[p * O + dim];
-            RawDyn raw{a.raw, a.B, 2 * a.c.D, p};
+            RawDyn raw(a.raw, a.B, 2 * a.c.D, p);
             EnvDimOut d = env_dim(a.c, raw, dim, member, obs_d, eps);
             sh.kl[threadIdx.x] = d.kl; sh.epv[threadIdx.x] = d.epv; sh.nx[threadIdx.x] = d.nx;
             sh.fin[threadIdx.x] = isfinite(d.nx) ? 1 : 0;
         }
         __syncthreads();
         if (active && dim == 0) {
-            RawDyn raw{a.raw, a.B, 2 * a.c.D, p};
+            RawDyn raw(a.raw, a.B, 2 * a.c.D, p);
             EnvRowOut r = env_row_finish(a.c, raw, member, sh.kl + rb * O, sh.epv + rb * O, sh.nx + rb * O,
                                          sh.fin + rb * O);
             const float v = a.v[p], vc = a.vc[p];
@@ -266,18 +267,19 @@ __global__ void rollout_final_kernel(int64_t B, int O, const float* cur, const u
     if (b.final_obs) for (int o = 0; o < O; ++o) b.final_obs[p * O + o] = cur[p * O + o];
 }
 
-EnvRowCfg make_env_cfg(const Net& dyn, const cmbpo_env_cfg& e, int O) {
+EnvRowCfg make_env_cfg(const Net& dyn, const cmbpo_env_cfg& e, int O, int precision) {
     EnvRowCfg c;
     c.O = O; c.D = dyn.D; c.E = dyn.E;
     c.term_id = e.term_id; c.cost_id = e.cost_id; c.predicts_cost = e.predicts_cost;
     c.deterministic = e.deterministic; c.predicts_delta = e.predicts_delta;
+    c.kl_closed_form = (precision != CMBPO_PREC_FP32) ? 1 : 0;
     c.sig_out = dyn.sig_out; c.mu_out = dyn.mu_out; c.l2s_out = dyn.l2s_out; c.elite = dyn.elite;
     return c;
 }
 
 ValueHead make_head(const Net& n, const float* raw) {
     ValueHead h;
-    h.raw = raw; h.E = n.E;
+    h.raw = raw; h.E = n.E; h.ld = 1;
     h.mu_out = n.has_out ? n.mu_out : nullptr; h.sig_out = n.sig_out;
     return h;
 }
@@ -299,6 +301,23 @@ int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precis
     Net& v = ctx->nets[CMBPO_NET_V];
     Net& vc = ctx->nets[CMBPO_NET_VC];
     CMBPO_CHECK(v.loaded && vc.loaded, "value ensembles not loaded");
+    if (precision != CMBPO_PREC_FP32 && ctx->polnet.loaded) {
+        // tcgen05 path: actor + V + VC as ONE merged ensemble launch (policy_pack.cu)
+        Net& pn = ctx->polnet;
+        const int A = pn.dims[3];
+        CMBPO_CHECK(ctx->log_std && A <= CMBPO_MAX_ACT, "actor not loaded");
+        float* raw;
+        if (cmbpo_ws_get(ctx, 3, (size_t)pn.E * a.N * A * sizeof(float), (void**)&raw)) return 1;
+        if (ens_forward(ctx, pn, a.obs, a.N, false, raw, precision)) return 1;
+        a.mu_raw = with_actor ? raw : nullptr;
+        a.log_std = ctx->log_std;
+        a.v = make_head(v, raw + (size_t)a.N * A); a.v.ld = A;
+        a.vc = make_head(vc, raw + (size_t)(1 + v.E) * a.N * A); a.vc.ld = A;
+        policy_rows_kernel<<<cdiv(a.N, 128), 128, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     float *raw_v, *raw_vc, *raw_mu = nullptr;
     if (cmbpo_ws_get(ctx, 3, (size_t)(v.E + vc.E) * a.N * sizeof(float), (void**)&raw_v)) return 1;
     raw_vc = raw_v + (size_t)v.E * a.N;
@@ -362,7 +381,7 @@ extern "C" int cmbpo_fakeenv_step(cmbpo_ctx* ctx, const cmbpo_env_cfg* cfg, cons
     if (cmbpo_ws_get(ctx, 2, (size_t)dyn.E * N * 2 * dyn.D * sizeof(float), (void**)&raw)) return 1;
     if (ens_forward(ctx, dyn, xin, N, false, raw, precision)) return 1;
     EnvStepArgs a = {};
-    a.N = N; a.O = O; a.A = A; a.c = make_env_cfg(dyn, *cfg, O); a.n_elite = dyn.n_elite;
+    a.N = N; a.O = O; a.A = A; a.c = make_env_cfg(dyn, *cfg, O, precision); a.n_elite = dyn.n_elite;
     a.obs = obs; a.raw = raw; a.elite_pos = elite_pos; a.state_eps = state_eps; a.path_ids = path_ids;
     a.seed = seed; a.step = step;
     a.next_obs = next_obs; a.rew = rew; a.cost = cost; a.term = term; a.dkl_path = dkl_path;
@@ -418,7 +437,7 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
         if (ens_forward(ctx, dyn, xin, B, false, raw, cfg->precision)) return 1;
         StepArgs sa = {};
         sa.B = B; sa.O = O; sa.A = A; sa.T = T; sa.t = t; sa.last_storable = T - 2;
-        sa.c = make_env_cfg(dyn, cfg->env, O); sa.n_elite = dyn.n_elite;
+        sa.c = make_env_cfg(dyn, cfg->env, O, cfg->precision); sa.n_elite = dyn.n_elite;
         sa.uncertainty = cfg->uncertainty_mode; sa.dkl_lim = cfg->dkl_lim;
         sa.path_base = cfg->path_id_base; sa.seed = cfg->seed;
         sa.raw = raw; sa.cur_obs = cur; sa.alive = alive; sa.pending = pending;

@@ -87,47 +87,13 @@ __device__ inline float np_sum_f32(const float (&a)[MAXN], int n) {
 }
 
 // ------------------------------------------------------------------------------------------
-// models/statics.py
-// ------------------------------------------------------------------------------------------
-// antsafe "notdone" with the precedence exactly as written (statics.py:24-27): the boolean
-// health flags multiply z_rot before the >= -0.7 comparison.
-template <int MAXO>
-__device__ inline bool antsafe_notdone(const float (&nx)[MAXO], int O) {
-    bool fin = true;
-    for (int o = 0; o < O; ++o) fin = fin && isfinite(nx[o]);
-    float z = nx[0];
-    float q1 = nx[2], q2 = nx[3];
-    float zrot = __fsub_rn(1.0f, __fmul_rn(2.0f, __fadd_rn(__fmul_rn(q1, q1), __fmul_rn(q2, q2))));
-    bool flags = fin && (z >= 0.2f) && (z <= 1.0f);
-    float prod = __fmul_rn(flags ? 1.0f : 0.0f, zrot);   // False * nan = nan, as in numpy
-    return prod >= -0.7f;
-}
-
-template <int MAXO>
-__device__ inline void apply_statics(int term_id, int cost_id, const float (&nx)[MAXO], int O,
-                                     bool& term, float& cost) {
-    bool done = false;
-    if (term_id == CMBPO_TERM_ANTSAFE) done = !antsafe_notdone(nx, O);           // statics.py:17-31
-    term = done;
-    if (cost_id == CMBPO_COST_HCS) {                                              // statics.py:10-15
-        float xd = __fmul_rn(nx[O - 1], 10.0f);
-        cost = (fabsf(xd) < 2.0f) ? 1.0f : 0.0f;
-    } else if (cost_id == CMBPO_COST_ANTSAFE) {                                   // statics.py:33-53
-        bool d2 = !antsafe_notdone(nx, O);
-        float c = (d2 ? 1.0f : 0.0f) + ((fabsf(nx[O - 1]) > 3.2f) ? 1.0f : 0.0f);
-        cost = fminf(fmaxf(c, 0.0f), 1.0f);
-    } else {
-        cost = 0.0f;                                                              // fake_env.py:146
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // FakeEnv.step for one row (fake_env.py:104-153) given the raw last-layer outputs of all E
 // members.  `raw(e, c)` returns column c of member e for this row (c < 2*D).
 // ------------------------------------------------------------------------------------------
 struct EnvRowCfg {
     int O, D, E;                 // D = O + 1 (+1 if the model predicts the cost)
     int term_id, cost_id, predicts_cost, deterministic, predicts_delta;
+    int kl_closed_form;          // 1: O(E) closed form of the pairwise KL sum (tensor-core precision modes)
     const float* sig_out;        // [D] max(sqrt(var),1e-2)   (pens/utils.py:167)
     const float* mu_out;         // [D]
     const float* l2s_out;        // [D] 2*log(sigma)          (pens/utils.py:187)
@@ -193,14 +159,16 @@ __device__ inline float np_sum_ptr(const float* a, int n) {
 // ------------------------------------------------------------------------------------------
 struct EnvDimOut { float kl, epv, nx; };
 
-template <class Raw>
-__device__ inline EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o, int member, float obs_o, float eps) {
-    const int E = c.E;
-    float nd[CMBPO_MAX_E], ls[CMBPO_MAX_E], vr[CMBPO_MAX_E], rv[CMBPO_MAX_E];
+// EC > 0: ensemble size known at compile time (loops fully unrolled, no predicates); EC == 0: runtime E
+template <int EC, class Raw>
+__device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int o, int member, float obs_o, float eps) {
+    constexpr int EMAX = EC > 0 ? EC : CMBPO_MAX_E;
+    const int E = EC > 0 ? EC : c.E;
+    float nd[EMAX], ls[EMAX], vr[EMAX], rv[EMAX];
     const float sg = c.sig_out[o], mu = c.mu_out[o], l2s = c.l2s_out[o];
     float sel = 0.f;
 #pragma unroll
-    for (int e = 0; e < CMBPO_MAX_E; ++e) {
+    for (int e = 0; e < EMAX; ++e) {
         if (e < E) {
             const float mean = __fadd_rn(__fmul_rn(sg, raw(e, o)), mu);          // pe.py:815-821
             const float logvar = __fadd_rn(l2s, raw(e, c.D + o));                // pe.py:826-828
@@ -214,31 +182,53 @@ __device__ inline EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o, int memb
             else if (isinf(var)) { l = 1e8f; }                                   // clip at 1e8 -> exp(2e8) = inf
             if (logvar != logvar) { l = logvar; v2 = logvar; }
             ls[e] = l; vr[e] = v2;
-            rv[e] = __frcp_rn(__fadd_rn(v2, 1e-10f));
+            rv[e] = __fdividef(1.0f, __fadd_rn(v2, 1e-10f));
             if (e == member) sel = x;
         }
     }
     // np.var over the member axis (fake_env.py:112): sequential sums, true divides
     float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < CMBPO_MAX_E; ++e) if (e < E) s = (e == 0) ? nd[0] : __fadd_rn(s, nd[e]);
+    for (int e = 0; e < EMAX; ++e) if (e < E) s = (e == 0) ? nd[0] : __fadd_rn(s, nd[e]);
     const float m = __fdiv_rn(s, (float)E);
     float q = 0.f;
 #pragma unroll
-    for (int e = 0; e < CMBPO_MAX_E; ++e) if (e < E) {
+    for (int e = 0; e < EMAX; ++e) if (e < E) {
         const float d = __fsub_rn(nd[e], m);
         const float d2 = __fmul_rn(d, d);
         q = (e == 0) ? d2 : __fadd_rn(q, d2);
     }
     EnvDimOut out;
     out.epv = __fdiv_rn(q, (float)E);
+    if (c.kl_closed_form) {
+        // sum_{i,j} KL(N_i||N_j) without the O(E^2) loop: the log-std terms cancel and
+        // sum_i (mu_j-mu_i)^2 = E d_j^2 + Q with d = mu - mean(mu), Q = sum d_i^2, so
+        //   sum = 0.5 * sum_j (E d_j^2 + Q + sum_i var_i) / (var_j + 1e-10) - 0.5 E^2 .
+        // Equal to the pairwise form up to float32 rounding (each pair is >= 0 analytically, so the
+        // reference's per-pair clip at 0 only removes rounding noise); used by the throughput modes.
+        float sv = 0.f;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) if (e < E) sv += vr[e];
+        const float qs = q + sv;
+        float acc2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) if (e < E) {
+            const float d = nd[e] - m;
+            acc2 = fmaf(fmaf((float)E * d, d, qs), rv[e], acc2);
+        }
+        float tot = fmaf(0.5f, acc2, -0.5f * (float)(E * E));
+        tot = (tot != tot) ? tot : fminf(fmaxf(tot, 0.0f), 1e10f * (float)(E * E));
+        out.kl = __fdiv_rn(tot, (float)((double)(E * (E - 1)) + 1e-10));
+        out.nx = c.predicts_delta ? __fadd_rn(sel, obs_o) : sel;
+        return out;
+    }
     // average_dkl (pens/utils.py:30-57): all ordered pairs, i outer / j inner
     float acc = 0.f;
     bool first = true;
 #pragma unroll
-    for (int i = 0; i < CMBPO_MAX_E; ++i) {
+    for (int i = 0; i < EMAX; ++i) {
 #pragma unroll
-        for (int j = 0; j < CMBPO_MAX_E; ++j) {
+        for (int j = 0; j < EMAX; ++j) {
             if (i < E && j < E) {
                 const float dm = __fsub_rn(nd[j], nd[i]);
                 const float ratio = __fmul_rn(__fadd_rn(__fmul_rn(dm, dm), vr[i]), rv[j]);
@@ -252,6 +242,16 @@ __device__ inline EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o, int memb
     out.kl = __fdiv_rn(acc, (float)((double)(E * (E - 1)) + 1e-10));             // pens/utils.py:56
     out.nx = c.predicts_delta ? __fadd_rn(sel, obs_o) : sel;                     // fake_env.py:125-131
     return out;
+}
+
+template <class Raw>
+__device__ inline EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o, int member, float obs_o, float eps) {
+    switch (c.E) {                      // the ensemble sizes the configs use (7 dynamics members; 5; 3)
+        case 7: return env_dim_t<7>(c, raw, o, member, obs_o, eps);
+        case 5: return env_dim_t<5>(c, raw, o, member, obs_o, eps);
+        case 3: return env_dim_t<3>(c, raw, o, member, obs_o, eps);
+        default: return env_dim_t<0>(c, raw, o, member, obs_o, eps);
+    }
 }
 
 // row-owner part: ordered reductions over the O dimensions (numpy order), statics, reward
