@@ -53,6 +53,7 @@ struct Net {
     void* tc_pack[3] = {nullptr, nullptr, nullptr};   // per precision (index = CMBPO_PREC_*)
     size_t tc_pack_bytes[3] = {0, 0, 0};
     float* tc_bias = nullptr;   // biases re-laid for the epilogue
+    int tc_group = 1;           // members per tcgen05 work unit (4 for narrow ensembles)
     // merged nets only: hidden activation per member (CMBPO_ACT_*); all -1 for an ordinary ensemble
     int member_act[CMBPO_MAX_E] = {-1, -1, -1, -1, -1, -1, -1, -1};
 };

@@ -38,7 +38,7 @@ constexpr int NS2 = 2;
 constexpr int XA_BYTES = 16384;   // [128 rows x 64 k x 2 B]
 
 struct Stage {        // one weight tile image in the packed stream
-    int layer, n0, k0, rows;
+    int layer, n0, k0, rows, member;   // member: index inside a group (0 for ordinary nets)
     unsigned long long off;
 };
 
@@ -171,10 +171,16 @@ __device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, float b
     }
 }
 
-template <int HD, int FMT, int ACT, bool DBG>
+// G > 1: GROUPED mode for narrow members (width HD/G): G members form one unit whose layer 0 is one
+// dense HD-wide layer (all chunks share the XA panel) and whose layers 1-2 are block diagonal (chunk j
+// belongs to member j / (NC/G), uses only that member's K panels and accumulates into that member's
+// OUT block).  A narrow net processed alone is a serial chain of tiny MMAs and drains; grouped, the
+// chunks of G members flow through the same double-buffered pipeline as one wide member.
+template <int HD, int FMT, int ACT, bool DBG, int G>
 __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams p) {
     constexpr int NC = HD / 64;                     // 64-column chunks of a hidden layer
-    constexpr int KP = HD / 64;                     // 64-wide K panels of layer 1
+    constexpr int KP = HD / 64 / G;                 // 64-wide K panels of layer 1 (per member)
+    constexpr int CPM = NC / G;                     // chunks per member
     constexpr int TPS = KP < 4 ? KP : 4;            // layer-1 tiles (K panels) per main-ring stage
     constexpr int G0 = NC < 4 ? NC : 4;             // layer-0 chunk tiles per main-ring stage
     constexpr uint32_t COL_H1 = 0, COL_D = HD / 2, COL_H2 = COL_D + 128;
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = p.role_mode ? (hw_warp + 4) % 20 : hw_warp;   // logical role id: 0-3 control, 4-19 epilogue
     const int nh2 = (p.parts == 1) ? 2 : 1;                    // H2 buffers (TMEM budget)
-    const uint32_t col_out = 512u - (uint32_t)p.NP;            // OUT occupies the top NP columns
+    const uint32_t col_out = 512u - (uint32_t)(p.NP * G);      // OUT occupies the top G*NP columns
     const int NPp = p.NP / p.parts;
     const uint32_t w2_chunk_bytes = (uint32_t)p.NP * 128u;     // all parts of one chunk
     if (warp == 1 && lane == 0) {
@@ -222,7 +228,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     // per CTA, so the last wave is balanced to within one member (a tile-granular split leaves the
     // last of ceil(782/148) = 6 rounds 72% empty), and neighbouring CTAs start on different members,
     // which spreads the weight streaming over E x more L2 addresses.
-    const long long n_units = (long long)p.ntiles * p.E;
+    const int n_groups = (p.E + G - 1) / G;         // E itself when G == 1
+    const long long n_units = (long long)p.ntiles * n_groups;
     const long long u0 = n_units * blockIdx.x / gridDim.x, u1 = n_units * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == 0) {
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         const long long t_begin = DBG ? clock64() : 0;
         for (long long u = u0; u < u1; ++u) {
             {
-                const int e = (int)(u % p.E);
+                const int e = (int)(u % n_groups);
                 const uint8_t* src = p.wmain + (unsigned long long)e * p.main_bytes;
                 auto push = [&](uint32_t bytes) {
                     wait_t<DBG>(bar + W_EMPTY + s, ph ^ 1, c_wempty);
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         unsigned long long dummy = 0;
         for (long long u = u0; u < u1; ++u) {
             {
-                const int e = (int)(u % p.E);
+                const int e = (int)(u % n_groups);
                 const uint8_t* src = p.w2 + (unsigned long long)e * p.w2_bytes;
                 for (int j0 = 0; j0 < NC; j0 += p.cps) {
                     const int nchunks = (NC - j0) < p.cps ? (NC - j0) : p.cps;
@@ -300,8 +307,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     const uint64_t dB = dW2 + (uint64_t)((s2 * W2SLOT + (jin * p.parts + q) * NPp * 128) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        mma_f16_ts(tmem + col_out + q * NPp, tmem + COL_H2 + hb * 32 + ks * 8, dB + 2 * ks, idesc_o,
-                                   !(jj == 0 && ks == 0));
+                        mma_f16_ts(tmem + col_out + (jj / CPM) * p.NP + q * NPp, tmem + COL_H2 + hb * 32 + ks * 8,
+                                   dB + 2 * ks, idesc_o, !(jj % CPM == 0 && ks == 0));
                 }
                 mma_commit(bar + H2_EMPTY + hb);
                 if (last_in_slot) mma_commit(bar + W2_EMPTY + s2);
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         };
         int cur_tile = -1;
         for (long long u = u0; u < u1; ++u) {
-            const int tile = (int)(u / p.E);
+            const int tile = (int)(u / n_groups);
             if (tile != cur_tile) {                 // a new row tile: its XA panel must have landed
                 cur_tile = tile;
                 wait_t<DBG>(bar + X_FULL, it & 1, c_x);
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
 #pragma unroll
                             for (int tt = 0; tt < TPS; ++tt) {
                                 const uint64_t dB = dW0 + (uint64_t)((s * STAGE + tt * TILE) >> 4);
-                                const uint32_t aT = tmem + COL_H1 + (kq * TPS + tt) * 32;
+                                const uint32_t aT = tmem + COL_H1 + ((j / CPM) * KP + kq * TPS + tt) * 32;
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)
                                     mma_f16_ts(tmem + COL_D + buf * 64, aT + ks * 8, dB + 2 * ks, idesc_h,
@@ -396,13 +403,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         const long long t_begin = DBG ? clock64() : 0;
         // deferred OUT epilogue: the four warpgroups split the NP output columns (16 or 32 each)
         int prev_e = 0; long long prev_grow = 0; uint32_t prev_m = 0; bool have_prev = false;
-        const int out_cw = (p.NP <= 64) ? 16 : 32;
+        const int out_cw = (G > 1) ? p.NP : ((p.NP <= 64) ? 16 : 32);
         auto out_epilogue = [&]() {
             wait_t<DBG>(bar + OUT_FULL, prev_m & 1, c_outw);
             tc_fence_after();
             const int c_begin = wg * out_cw;
             uint32_t r[32];
-            const bool mine = c_begin < p.NP;
+            const bool mine = (G > 1) ? (wg < G && prev_e * G + wg < p.E) : (c_begin < p.NP);
             if (mine) {
                 tmem_ld16(tmem + col_out + c_begin + lane_base, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
                 if (out_cw == 32) tmem_ld16(tmem + col_out + c_begin + 16 + lane_base, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
@@ -412,12 +419,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             __syncwarp();
             if (lane == 0) mbar_arrive(bar + OUT_EMPTY);          // accumulator free again (16 warps arrive)
             if (mine && prev_grow < p.N) {
-                float* orow = p.out + (long long)prev_e * p.out_member_stride + prev_grow * p.Nout;
-                const float* b2 = p.bias + (long long)prev_e * p.bias_stride + 2 * HD;
+                const int cb = (G > 1) ? 0 : c_begin;          // first output column of this warpgroup's slice
+                float* orow = p.out + (long long)(prev_e * G + (G > 1 ? wg : 0)) * p.out_member_stride + prev_grow * p.Nout;
+                const float* b2 = p.bias + (long long)prev_e * p.bias_stride + 2 * HD + (G > 1 ? wg * p.NP : 0);
                 if ((p.Nout & 3) == 0) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const int c = c_begin + i;
+                        const int c = cb + i;
                         if (i < out_cw && c < p.Nout) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + c));
                             float4 v;
@@ -429,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int c = c_begin + i;
+                        const int c = cb + i;
                         if (i < out_cw && c < p.Nout) orow[c] = __uint_as_float(r[i]) + b2[c];
                     }
                 }
@@ -439,7 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         int cur_tile = -1;
         long long grow = 0;
         for (long long u = u0; u < u1; ++u) {
-            const int tile = (int)(u / p.E);
+            const int tile = (int)(u / n_groups);
             const bool new_tile = tile != cur_tile;
             cur_tile = tile;
             grow = (long long)tile * 128 + row;
@@ -469,9 +477,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 if (lane == 0) mbar_arrive(bar + X_FULL);
             }
             {
-                const int e = (int)(u % p.E);
+                const int e = (int)(u % n_groups);
                 const float* bias = p.bias + (long long)e * p.bias_stride;
-                const int act_e = (ACT == 0) ? p.member_act[e] : ACT;
                 // Each pair drains every other chunk (chunk j <-> accumulator buffer j&1 <-> pair), so the
                 // loops below run over this pair's chunks only.  The bias of the NEXT drain (lane l holds
                 // bias[l] of this warp's 32 columns) is loaded one drain ahead: its latency hides behind
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     tc_fence_after();
                     if (half == 0) { TRACE(1 + pair, 1000 + j); }
                     const long long td = DBG ? clock64() : 0;
-                    drain32_act<FMT, ACT>(act_e, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
+                    drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
                                       tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0, p.act_x2 != 0);
                     if (DBG) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
@@ -510,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     tc_fence_after();
                     if (half == 0) { TRACE(1 + pair, 2000 + j); }
                     const long long td = DBG ? clock64() : 0;
-                    drain32_act<FMT, ACT>(act_e, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
+                    drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
                                       tmem + COL_H2 + hb * 32 + half * 16 + lane_base, bar + D_EMPTY + buf,
                                       bar + H2_EMPTY + hb, (hn & 1) ^ 1, p.act_x2 != 0);
                     if (DBG) c_drain += (unsigned long long)(clock64() - td);
@@ -542,15 +549,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
 // neuron n0+n, 64 consecutive k from k0; zero padded.
 template <int FMT>
 __global__ void pack_weights_kernel(const float* W0, const float* W1, const float* W2, int K0, int HD,
-                                    int Nout, const Stage* stages, int n_stages,
+                                    int Nout, int E, int group, const Stage* stages, int n_stages,
                                     unsigned long long member_bytes, uint8_t* out) {
-    const int e = blockIdx.y;
     const Stage st = stages[blockIdx.x];
+    const int e = blockIdx.y * group + st.member;        // real member (may be >= E in the last group: zeros)
     const float* W; int K, M;
     if (st.layer == 0) { W = W0 + (size_t)e * K0 * HD; K = K0; M = HD; }
     else if (st.layer == 1) { W = W1 + (size_t)e * HD * HD; K = HD; M = HD; }
     else { W = W2 + (size_t)e * HD * Nout; K = HD; M = Nout; }
-    uint8_t* dst = out + (size_t)e * member_bytes + st.off;
+    if (e >= E) K = 0;
+    uint8_t* dst = out + (size_t)blockIdx.y * member_bytes + st.off;
     for (int idx = threadIdx.x; idx < st.rows * 64; idx += blockDim.x) {
         const int n = idx >> 6, k = idx & 63;
         const int gk = st.k0 + k, gn = st.n0 + n;
@@ -562,16 +570,24 @@ __global__ void pack_weights_kernel(const float* W0, const float* W1, const floa
     }
 }
 
+// per unit: [b0 of the G members | b1 of the G members | b2 (NP each) of the G members]; HD = member width
 __global__ void pack_bias_kernel(const float* b0, const float* b1, const float* b2, int HD, int Nout, int NP,
-                                 float* out) {
-    const int e = blockIdx.x;
-    const int stride = 2 * HD + NP;
+                                 int E, int group, float* out) {
+    const int u = blockIdx.x;
+    const int stride = group * (2 * HD + NP);
     for (int i = threadIdx.x; i < stride; i += blockDim.x) {
-        float v;
-        if (i < HD) v = b0[(size_t)e * HD + i];
-        else if (i < 2 * HD) v = b1[(size_t)e * HD + i - HD];
-        else v = (i - 2 * HD < Nout) ? b2[(size_t)e * Nout + i - 2 * HD] : 0.f;
-        out[(size_t)e * stride + i] = v;
+        float v = 0.f;
+        if (i < group * HD) {
+            const int e = u * group + i / HD;
+            if (e < E) v = b0[(size_t)e * HD + i % HD];
+        } else if (i < 2 * group * HD) {
+            const int k = i - group * HD, e = u * group + k / HD;
+            if (e < E) v = b1[(size_t)e * HD + k % HD];
+        } else {
+            const int k = i - 2 * group * HD, e = u * group + k / NP, c = k % NP;
+            if (e < E && c < Nout) v = b2[(size_t)e * Nout + c];
+        }
+        out[(size_t)u * stride + i] = v;
     }
 }
 
@@ -584,17 +600,24 @@ OutShape out_shape(int Nout) {
 // the order in which the MMA warp consumes weight tiles (must match the kernel's loops):
 // main stream = layer-0 chunk tiles, then per chunk the layer-1 K-panel tiles; W2 stream = per chunk
 // the layer-2 tile(s)
-void stage_programs(int HD, int NP, int parts, std::vector<Stage>* main_prog, unsigned long long* main_bytes,
-                    std::vector<Stage>* w2_prog, unsigned long long* w2_bytes) {
-    const int NC = HD / 64, KP = HD / 64, NPp = NP / parts;
+void stage_programs(int HD, int NP, int parts, int group, std::vector<Stage>* main_prog,
+                    unsigned long long* main_bytes, std::vector<Stage>* w2_prog, unsigned long long* w2_bytes) {
+    // HD = virtual width of a unit (group * member width); chunk j belongs to member j / CPM
+    const int NC = HD / 64, CPM = NC / group, KPm = HD / 64 / group, NPp = NP / parts;
     unsigned long long off = 0;
-    for (int j = 0; j < NC; ++j) { main_prog->push_back(Stage{0, j * 64, 0, 64, off}); off += TILE; }
+    for (int j = 0; j < NC; ++j) { main_prog->push_back(Stage{0, (j % CPM) * 64, 0, 64, j / CPM, off}); off += TILE; }
     for (int j = 0; j < NC; ++j)
-        for (int kp = 0; kp < KP; ++kp) { main_prog->push_back(Stage{1, j * 64, kp * 64, 64, off}); off += TILE; }
+        for (int kp = 0; kp < KPm; ++kp) {
+            main_prog->push_back(Stage{1, (j % CPM) * 64, kp * 64, 64, j / CPM, off});
+            off += TILE;
+        }
     *main_bytes = off;
     off = 0;
     for (int j = 0; j < NC; ++j)
-        for (int q = 0; q < parts; ++q) { w2_prog->push_back(Stage{2, q * NPp, j * 64, NPp, off}); off += (unsigned long long)NPp * 128; }
+        for (int q = 0; q < parts; ++q) {
+            w2_prog->push_back(Stage{2, q * NPp, (j % CPM) * 64, NPp, j / CPM, off});
+            off += (unsigned long long)NPp * 128;
+        }
     *w2_bytes = off;
 }
 
@@ -606,13 +629,13 @@ int chunks_per_w2_slot(int HD, int NP) {
     return p2 < NC ? p2 : NC;
 }
 
-template <int HD, int FMT, int ACT, bool DBG>
+template <int HD, int FMT, int ACT, bool DBG, int G = 1>
 int launch_tc(cmbpo_ctx* ctx, const TcParams& p) {
     const int smem = SMEM_TOTAL + 1024 + (DBG ? 1568 : 0);
     static_assert(SMEM_TOTAL + 1024 + 1568 <= 232448, "shared memory budget");
-    auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT, DBG>;
+    auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT, DBG, G>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const long long units = (long long)p.ntiles * p.E;
+    const long long units = (long long)p.ntiles * ((p.E + G - 1) / G);
     const int grid = units < ctx->sm_count ? (int)units : ctx->sm_count;
     kern<<<grid, NTHREADS, smem, ctx->stream>>>(p);
     ctx->launches++;
@@ -625,6 +648,13 @@ int launch_tc_act(cmbpo_ctx* ctx, const TcParams& p, int act) {
     if (act == 0) return launch_tc<HD, FMT, 0, false>(ctx, p);
     if (act == CMBPO_ACT_SWISH) return launch_tc<HD, FMT, CMBPO_ACT_SWISH, false>(ctx, p);
     return launch_tc<HD, FMT, CMBPO_ACT_TANH, false>(ctx, p);
+}
+
+template <int FMT>
+int launch_tc_grouped(cmbpo_ctx* ctx, const TcParams& p, int act) {       // 4 members of width 128 per unit
+    if (act == 0) return launch_tc<512, FMT, 0, false, 4>(ctx, p);
+    if (act == CMBPO_ACT_SWISH) return launch_tc<512, FMT, CMBPO_ACT_SWISH, false, 4>(ctx, p);
+    return launch_tc<512, FMT, CMBPO_ACT_TANH, false, 4>(ctx, p);
 }
 
 template <int FMT>
@@ -650,31 +680,35 @@ bool ens_tc_supported(const Net& n) {
 int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
     const int HD = net.dims[1], K0 = net.dims[0], Nout = net.dims[3];
     const OutShape os = out_shape(Nout);
+    // narrow ensembles run grouped: 4 members of width 128 per unit (their OUT blocks share 64 columns)
+    const int group = (HD == 128 && net.E >= 2 && os.NP <= 16) ? 4 : 1;
+    const int n_units = (net.E + group - 1) / group;
+    net.tc_group = group;
     unsigned long long main_bytes = 0, w2_bytes = 0;
     std::vector<Stage> mp, wp;
-    stage_programs(HD, os.NP, os.parts, &mp, &main_bytes, &wp, &w2_bytes);
+    stage_programs(HD * group, os.NP, os.parts, group, &mp, &main_bytes, &wp, &w2_bytes);
     Stage *d_mp, *d_wp;
     CUDA_TRY(cudaMalloc(&d_mp, mp.size() * sizeof(Stage)));
     CUDA_TRY(cudaMalloc(&d_wp, wp.size() * sizeof(Stage)));
     CUDA_TRY(cudaMemcpyAsync(d_mp, mp.data(), mp.size() * sizeof(Stage), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(d_wp, wp.data(), wp.size() * sizeof(Stage), cudaMemcpyHostToDevice, ctx->stream));
     for (int prec = CMBPO_PREC_BF16; prec <= CMBPO_PREC_FP16; ++prec) {
-        const size_t total = (size_t)net.E * (main_bytes + w2_bytes);
+        const size_t total = (size_t)n_units * (main_bytes + w2_bytes);
         CUDA_TRY(cudaMalloc(&net.tc_pack[prec], total));
         net.tc_pack_bytes[prec] = (size_t)main_bytes;       // W2 stream starts at E * main_bytes
         uint8_t* base = (uint8_t*)net.tc_pack[prec];
-        uint8_t* base2 = base + (size_t)net.E * main_bytes;
-        dim3 g1((unsigned)mp.size(), net.E), g2((unsigned)wp.size(), net.E);
+        uint8_t* base2 = base + (size_t)n_units * main_bytes;
+        dim3 g1((unsigned)mp.size(), n_units), g2((unsigned)wp.size(), n_units);
         if (prec == CMBPO_PREC_FP16) {
-            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_mp, (int)mp.size(), main_bytes, base);
-            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_wp, (int)wp.size(), w2_bytes, base2);
+            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, base);
+            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, base2);
         } else {
-            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_mp, (int)mp.size(), main_bytes, base);
-            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, d_wp, (int)wp.size(), w2_bytes, base2);
+            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, base);
+            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, base2);
         }
     }
-    CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)net.E * (2 * HD + os.NP) * sizeof(float)));
-    pack_bias_kernel<<<net.E, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, Nout, os.NP, net.tc_bias);
+    CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)n_units * group * (2 * HD + os.NP) * sizeof(float)));
+    pack_bias_kernel<<<n_units, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, Nout, os.NP, net.E, group, net.tc_bias);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaFree(d_mp));
     CUDA_TRY(cudaFree(d_wp));
@@ -694,12 +728,13 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     TcParams p;
     p.Nout = net.dims[3];
     p.NP = os.NP; p.parts = os.parts;
-    p.cps = chunks_per_w2_slot(HD, os.NP);
+    p.cps = chunks_per_w2_slot(HD * net.tc_group, os.NP);
     p.wmain = (const uint8_t*)net.tc_pack[precision];
     p.main_bytes = net.tc_pack_bytes[precision];
-    p.w2 = p.wmain + (size_t)net.E * p.main_bytes;
-    p.w2_bytes = (unsigned long long)(HD / 64) * p.NP * 128;
-    p.bias = net.tc_bias; p.bias_stride = 2 * HD + p.NP;
+    p.w2 = p.wmain + (size_t)((net.E + net.tc_group - 1) / net.tc_group) * p.main_bytes;
+    p.w2_bytes = (unsigned long long)(HD * net.tc_group / 64) * p.NP * 128;
+    const int group = net.tc_group, n_units = (net.E + group - 1) / group;
+    p.bias = net.tc_bias; p.bias_stride = group * (2 * HD + p.NP);
     p.E = net.E; p.K0 = net.dims[0]; p.KS0 = (p.K0 + 15) / 16;
     p.x = x; p.N = N; p.ldx = net.dims[0];
     p.mu_in = net.has_in ? net.mu_in : nullptr; p.sig_in = net.sig_in;
@@ -743,6 +778,8 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
         }
         return 0;
     }
+    (void)n_units;
+    if (group == 4) return precision == CMBPO_PREC_FP16 ? launch_tc_grouped<0>(ctx, p, act_sel) : launch_tc_grouped<1>(ctx, p, act_sel);
     if (precision == CMBPO_PREC_FP16) return launch_tc_hd<0>(ctx, p, HD, act_sel);
     return launch_tc_hd<1>(ctx, p, HD, act_sel);
 }

@@ -1,6 +1,6 @@
 """Debug aid: per-CTA protocol timing of the tcgen05 ensemble kernel (CMBPO_TC_DEBUG=1)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import cmbpo_b200 as cb
