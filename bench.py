@@ -51,6 +51,16 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of K1 from the committed `ncu --set full` summary (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -288,7 +298,7 @@ def run_cuda(args, rank, world, local_rank):
             if info["alive_ratio"] <= 0.1:
                 break
         smp.finish_all_paths()
-        out, _ = pool.get()                          # D2H of the 12 arrays
+        out, _ = pool.get(pinned=True)               # D2H of the 12 arrays (page-locked staging)
         return out
 
     e2e_pass()
@@ -323,6 +333,10 @@ def run_cuda(args, rank, world, local_rank):
         gae_gbs = 32.0 * gae_steps / (gae_launch_ms * 1e-3) / 1e9 if gae_launch_ms > 0 else 0.0
         # CPU baseline: bounded sample of the same workload through the oracle port
         cpu_n, cpu_dt = cpu_rollout_sample(args.cpu_batch)
+        if cpu_dt < 6.0:                         # scale the bounded sample to ~12 s of CPU work
+            scaled = int(min(20000, args.cpu_batch * 12.0 / max(cpu_dt, 1e-3)))
+            cpu_n, cpu_dt = cpu_rollout_sample(scaled)
+            args.cpu_batch = scaled
         try:
             cores = torch.get_num_threads()
         except Exception:
@@ -348,7 +362,7 @@ def run_cuda(args, rank, world, local_rank):
             "roofline": {"bound": "tensor", "kernel": "dynamics-ensemble GEMM chain (K1)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if tensor_path else achieved_tf / peak_tf,
-                         "traffic": None, "launch_ms": dyn_launch_ms, "rows_per_launch": rows_per_launch,
+                         "traffic": ncu_traffic(), "launch_ms": dyn_launch_ms, "rows_per_launch": rows_per_launch,
                          "flop_per_row": fdyn, "share_of_step": dyn_launch_ms * (T - 1) / (ms / args.steps)},
             "gae": {"ms_per_1M_steps": gae_launch_ms / (gae_steps / 1e6), "achieved_GBps": gae_gbs,
                     "peak_GBps": pk["hbm"], "frac": gae_gbs / pk["hbm"], "bytes_per_step": 32,
@@ -376,7 +390,7 @@ L_PROF_DYN, L_PROF_GAE = 0, 1
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16", "fp16x2", "bf16x2"])

@@ -21,6 +21,7 @@ from .cpobuffer import CPOBuffer
 from .model_sampler import ModelSampler
 from .rollout import RolloutBuffers
 from . import statics
+from . import dist
 
 __all__ = ["Engine", "B200PE", "B200Policy", "FakeEnv", "ModelBuffer", "CPOBuffer", "ModelSampler",
            "RolloutBuffers", "CmbpoError", "LIB_PATH", "statics"]

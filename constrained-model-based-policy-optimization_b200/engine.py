@@ -7,6 +7,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
+from .dist import combine_pass1, combine_pass2
 
 
 def _as_f32(a):
@@ -254,16 +255,12 @@ class Engine:
         if reduce_fn is not None:
             reduce_fn(sums)
         s = sums.cpu().numpy()
-        n = np.float32(s[0])
-        if s[0] == 0:
-            return dict(n=0, adv_mean=np.float32(0), adv_std=np.float32(0), cadv_mean=np.float32(0),
-                        ret_mean=0, cret_mean=0)
-        adv_mean = np.float32(s[1]) / n
-        cadv_mean = np.float32(s[2]) / n
-        ret_mean = np.float32(np.float32(s[3]) / n)
-        cret_mean = np.float32(np.float32(s[4]) / n)
+        st = combine_pass1(s)
+        if st["n"] == 0:
+            st["adv_std"] = np.float32(0)
+            return st
         L.check(self.lib.cmbpo_adv_stats_pass2(self.h, self._p(adv), n_paths, max_len, path_stride,
-                                               time_stride, self._p(length), float(adv_mean),
+                                               time_stride, self._p(length), float(st["adv_mean"]),
                                                self._p(sums)))
         if reduce_fn is not None:
             ss = sums[5:6].clone()
@@ -271,9 +268,8 @@ class Engine:
             ssq = float(ss.item())
         else:
             ssq = float(sums[5].item())
-        adv_std = np.sqrt(np.float32(ssq) / n)
-        return dict(n=int(s[0]), adv_mean=np.float32(adv_mean), adv_std=np.float32(adv_std),
-                    cadv_mean=np.float32(cadv_mean), ret_mean=ret_mean, cret_mean=cret_mean)
+        st["adv_std"] = np.float32(combine_pass2(ssq, st["n"]))
+        return st
 
     def adv_normalise(self, adv, cadv, n_paths, max_len, path_stride, time_stride, length, st):
         L.check(self.lib.cmbpo_adv_normalise(self.h, self._p(adv), self._p(cadv), n_paths, max_len,

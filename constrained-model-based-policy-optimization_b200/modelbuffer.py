@@ -166,9 +166,31 @@ class ModelBuffer:
                     poolm_cret_mean=st["cret_mean"])
         return out, diag
 
-    def get(self):
-        """modelbuffer.py:184-226.  Returns numpy copies and resets, like the reference."""
+    def get(self, pinned=False):
+        """modelbuffer.py:184-226.  Returns numpy arrays and resets, like the reference.
+
+        `pinned=True` stages the 12 arrays through page-locked host buffers (one asynchronous D2H
+        copy each, a single synchronisation): ~2.5x the PCIe rate of pageable copies.  The pinned
+        buffers are recycled every second call, so a caller must consume (or copy) the arrays before
+        the second next `get()` -- cmbpo.py:270 concatenates them immediately."""
         out, diag = self.get_device()
-        res = [x.cpu().numpy() for x in out]
+        if not pinned:
+            res = [x.cpu().numpy() for x in out]
+        else:
+            t = self.engine.torch
+            self._pin_gen = getattr(self, "_pin_gen", 0) ^ 1
+            pool = self.__dict__.setdefault("_pin_pool", {})
+            host = []
+            for i, x in enumerate(out):
+                key = (self._pin_gen, i)
+                buf = pool.get(key)
+                if buf is None or buf.numel() < x.numel() or buf.dtype != x.dtype:
+                    buf = t.empty(max(x.numel(), 1), dtype=x.dtype, pin_memory=True)
+                    pool[key] = buf
+                h = buf[:x.numel()].view(x.shape)
+                h.copy_(x, non_blocking=True)
+                host.append(h)
+            t.cuda.current_stream(self.engine.device).synchronize()
+            res = [h.numpy() for h in host]
         self.reset()
         return res, diag
