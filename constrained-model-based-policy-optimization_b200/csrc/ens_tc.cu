@@ -123,47 +123,59 @@ __device__ __forceinline__ uint32_t activate_x2(float x0, float x1) {
 template <int FMT, int ACT>
 __device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32_t dst_addr,
                                         uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity,
-                                        bool x2) {
+                                        bool x2, uint32_t* tr = nullptr) {
     uint32_t r[32];
     tmem_ld32(d_addr, r);
     tmem_ld_wait();
+    if (tr) tr[0] = (uint32_t)clock64();
     tc_fence_before();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(d_empty);
     uint32_t q[16];
     // lane l holds bias[l] of this warp's 32 columns (one coalesced load issued BEFORE the accumulator
-    // wait; shared memory is carved to the limit so there is no L1 to serve per-thread bias loads)
+    // wait; shared memory is carved to the limit so there is no L1 to serve per-thread bias loads).
+    // The 32 elements are independent: straight-line code (no branch inside the loops) lets the
+    // scheduler overlap the shuffle / MUFU latencies of all of them.
+    float v[32];
+    if (!x2 && ACT == CMBPO_ACT_SWISH) {
+        // swish(x) = t + t tanh t with t = x/2 = fma(acc, 0.5, bias/2): 4.5 instructions per element
+        // (SHFL, FFMA, MUFU, FFMA, half a packed saturating convert)
+        const float hb = 0.5f * bias_lane;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float4 b;
-        b.x = __shfl_sync(0xffffffffu, bias_lane, 4 * c + 0);
-        b.y = __shfl_sync(0xffffffffu, bias_lane, 4 * c + 1);
-        b.z = __shfl_sync(0xffffffffu, bias_lane, 4 * c + 2);
-        b.w = __shfl_sync(0xffffffffu, bias_lane, 4 * c + 3);
-        if (x2) {
-            q[2 * c] = activate_x2<FMT, ACT>(__uint_as_float(r[4 * c + 0]) + b.x, __uint_as_float(r[4 * c + 1]) + b.y);
-            q[2 * c + 1] = activate_x2<FMT, ACT>(__uint_as_float(r[4 * c + 2]) + b.z, __uint_as_float(r[4 * c + 3]) + b.w);
-            continue;
-        }
-        const float v0 = activate<ACT>(__uint_as_float(r[4 * c + 0]) + b.x);
-        const float v1 = activate<ACT>(__uint_as_float(r[4 * c + 1]) + b.y);
-        const float v2 = activate<ACT>(__uint_as_float(r[4 * c + 2]) + b.z);
-        const float v3 = activate<ACT>(__uint_as_float(r[4 * c + 3]) + b.w);
-        q[2 * c] = Cvt<FMT>::pack(v0, v1);
-        q[2 * c + 1] = Cvt<FMT>::pack(v2, v3);
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), 0.5f, __shfl_sync(0xffffffffu, hb, i));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = swish_half(v[i]);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) q[c] = Cvt<FMT>::pack(v[2 * c], v[2 * c + 1]);
+        goto store;
     }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_lane, i);
+    if (x2) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) q[c] = activate_x2<FMT, ACT>(v[2 * c], v[2 * c + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(v[i]);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) q[c] = Cvt<FMT>::pack(v[2 * c], v[2 * c + 1]);
+    }
+store:
+    if (tr) tr[1] = (uint32_t)clock64();
     if (dst_free) { mbar_wait(dst_free, dst_parity); tc_fence_after(); }
     tmem_st16(dst_addr, q);
     tmem_st_wait();
     tc_fence_before();
+    if (tr) tr[2] = (uint32_t)clock64();
 }
 
 // ACT == 0: the activation is a per-member runtime value (merged policy ensemble)
 template <int FMT, int ACT>
 __device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, float bias_lane, uint32_t dst_addr,
-                                            uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity, bool x2) {
+                                            uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity, bool x2,
+                                            uint32_t* tr = nullptr) {
     if (ACT != 0) {
-        drain32<FMT, ACT>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2);
+        drain32<FMT, ACT>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2, tr);
     } else if (act_rt == CMBPO_ACT_TANH) {
         drain32<FMT, CMBPO_ACT_TANH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2);
     } else {
@@ -232,6 +244,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     const long long n_units = (long long)p.ntiles * n_groups;
     const long long u0 = n_units * blockIdx.x / gridDim.x, u1 = n_units * (blockIdx.x + 1) / gridDim.x;
 
+    // Register re-balancing (per warpgroup): the control warpgroup needs few registers, the epilogue
+    // warps need enough to keep all 32 element chains of a drain in flight (at the 96 of the launch
+    // bound ptxas serialises them through one temporary: ~2000 instead of ~500 cycles per drain).
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ===== main weight producer: layer-0 and layer-1 tiles, 32 KB per stage =====
         uint32_t s = 0, ph = 0;
@@ -391,7 +408,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             d[2] = (unsigned long long)(clock64() - t_begin);
             d[3] = c_w; d[4] = c_d; d[5] = c_h1; d[6] = c_h2; d[7] = c_out; d[8] = c_x;
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ===== epilogue: 4 warpgroups; pair (wg>>1) owns accumulator buffer (wg>>1), half (wg&1) its columns =====
         const int wg = (warp - 4) >> 2;
         const uint32_t pair = (uint32_t)wg >> 1, half = (uint32_t)wg & 1;
@@ -400,6 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
         uint32_t g = 0, m = 0, c1 = 0;
         unsigned long long c_dfull = 0, c_drain = 0, c_outw = 0;
+        uint32_t dtr[3] = {0, 0, 0};
         const long long t_begin = DBG ? clock64() : 0;
         // deferred OUT epilogue: the four warpgroups split the NP output columns (16 or 32 each)
         int prev_e = 0; long long prev_grow = 0; uint32_t prev_m = 0; bool have_prev = false;
@@ -496,7 +516,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     if (half == 0) { TRACE(1 + pair, 1000 + j); }
                     const long long td = DBG ? clock64() : 0;
                     drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
-                                      tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0, p.act_x2 != 0);
+                                      tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0, p.act_x2 != 0,
+                                      DBG ? dtr : nullptr);
+                    if (DBG && half == 0 && pair == 0 && m == 8 && lane == 0 && (warp & 3) == 0 && p.dbg && blockIdx.x == 0) {
+                        uint32_t* t_ = trace_smem + 130; uint32_t n_ = t_[0];
+                        if (n_ + 3 <= 64) { for (int q_ = 0; q_ < 3; ++q_) { t_[2 + (n_ + q_) * 2] = 1200 + q_; t_[3 + (n_ + q_) * 2] = dtr[q_]; } t_[0] = n_ + 3; }
+                    }
                     if (DBG) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar + H1_FULL);
@@ -746,14 +771,16 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     const int act_sel = net.member_act[0] >= 0 ? 0 : net.acts[0];
     { static const char* rm = getenv("CMBPO_TC_ROLES"); p.role_mode = rm ? atoi(rm) : 0; }
     static const char* dbg_env = getenv("CMBPO_TC_DEBUG");
-    if (dbg_env && HD == 512 && net.acts[0] == CMBPO_ACT_SWISH && precision == CMBPO_PREC_FP16) {
+    const bool dbg_big = dbg_env && atoi(dbg_env) == 1 && HD == 512 && group == 1 && net.acts[0] == CMBPO_ACT_SWISH;
+    const bool dbg_grp = dbg_env && atoi(dbg_env) == 2 && group == 4 && act_sel == 0;
+    if ((dbg_big || dbg_grp) && precision == CMBPO_PREC_FP16) {
         // protocol timing: per-CTA cycle counters printed once per launch (debug aid, off by default)
         unsigned long long* d;
         const size_t dbg_words = 4096 + 3 * 1024;
         if (cmbpo_ws_get(ctx, 1, dbg_words * 8, (void**)&d)) return 1;
         CUDA_TRY(cudaMemsetAsync(d, 0, dbg_words * 8, ctx->stream));
         p.dbg = d;
-        if (launch_tc<512, 0, CMBPO_ACT_SWISH, true>(ctx, p)) return 1;
+        if (dbg_big ? launch_tc<512, 0, CMBPO_ACT_SWISH, true>(ctx, p) : launch_tc<512, 0, 0, true, 4>(ctx, p)) return 1;
         std::vector<unsigned long long> h(dbg_words);
         CUDA_TRY(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -162,10 +162,9 @@ __host__ __device__ constexpr uint32_t panel_off(int r, int c) {
 template <int FMT> struct Cvt;
 template <> struct Cvt<0> {   // fp16, saturating so a diverged rollout clamps instead of producing inf
     __device__ static uint32_t pack(float a, float b) {
-        a = fminf(fmaxf(a, -65504.f), 65504.f);
-        b = fminf(fmaxf(b, -65504.f), 65504.f);
-        __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
+        uint32_t d;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));   // d = {hi: b, lo: a}
+        return d;
     }
 };
 template <> struct Cvt<1> {   // bf16
@@ -185,9 +184,10 @@ __device__ __forceinline__ float swish_fast(float x) {
     float t = 0.5f * x;
     return fmaf(t, tanh_approx(t), t);
 }
+// same, for a pre-halved argument t = x/2
+__device__ __forceinline__ float swish_half(float t) { return fmaf(t, tanh_approx(t), t); }
 
 }  // namespace tc
-
 namespace tc {
 // D[tmem] (+)= A[tmem] * B[smem]^T : A operand read from tensor memory (lane = row, one 32-bit
 // column = two consecutive 16-bit K elements)
