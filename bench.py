@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -332,8 +332,9 @@ def run_cuda(args, rank, world, local_rank):
         gae_steps = B * (T - 1)
         gae_gbs = 32.0 * gae_steps / (gae_launch_ms * 1e-3) / 1e9 if gae_launch_ms > 0 else 0.0
         # CPU baseline: bounded sample of the same workload through the oracle port
-        cpu_n, cpu_dt = cpu_rollout_sample(args.cpu_batch)
-        if cpu_dt < 6.0:                         # scale the bounded sample to ~12 s of CPU work
+        # CPU baseline: rank 0 at N=1 only (under torchrun OMP_NUM_THREADS is pinned to 1)
+        cpu_n, cpu_dt = (0, 1.0) if world > 1 else cpu_rollout_sample(args.cpu_batch)
+        if world == 1 and cpu_dt < 6.0:                         # scale the bounded sample to ~12 s of CPU work
             scaled = int(min(20000, args.cpu_batch * 12.0 / max(cpu_dt, 1e-3)))
             cpu_n, cpu_dt = cpu_rollout_sample(scaled)
             args.cpu_batch = scaled
@@ -367,8 +368,9 @@ def run_cuda(args, rank, world, local_rank):
             "gae": {"ms_per_1M_steps": gae_launch_ms / (gae_steps / 1e6), "achieved_GBps": gae_gbs,
                     "peak_GBps": pk["hbm"], "frac": gae_gbs / pk["hbm"], "bytes_per_step": 32,
                     "steps_per_launch": gae_steps, "scan": "strict float64 sequential (bit-exact)"},
-            "cpu_baseline": {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d start states x %d steps (one pass, %.1f s)" % (args.cpu_batch, T - 1, cpu_dt)},
+            "cpu_baseline": ({"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
+                              "sample": "%d start states x %d steps (one pass, %.1f s)" % (args.cpu_batch, T - 1, cpu_dt)}
+                             if world == 1 else None),
             "e2e": {"value": e2e_n / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(obs_host.nbytes), "d2h_bytes_per_step": int(d2h),
                     "api": "ModelSampler.reset/sample/finish_all_paths + ModelBuffer.get (numpy in, numpy out)"},
