@@ -334,8 +334,9 @@ def run_cuda(args, rank, world, local_rank):
         gae_gbs = 32.0 * gae_steps / (gae_launch_ms * 1e-3) / 1e9 if gae_launch_ms > 0 else 0.0
         # CPU baseline: bounded sample of the same workload through the oracle port
         # CPU baseline: rank 0 at N=1 only (under torchrun OMP_NUM_THREADS is pinned to 1)
-        cpu_n, cpu_dt = (0, 1.0) if world > 1 else cpu_rollout_sample(args.cpu_batch)
-        if world == 1 and cpu_dt < 6.0:                         # scale the bounded sample to ~12 s of CPU work
+        skip_cpu = world > 1 or args.cpu_batch <= 0        # --cpu-batch 0: developer runs only
+        cpu_n, cpu_dt = (0, 1.0) if skip_cpu else cpu_rollout_sample(args.cpu_batch)
+        if not skip_cpu and cpu_dt < 6.0:                         # scale the bounded sample to ~12 s of CPU work
             scaled = int(min(20000, args.cpu_batch * 12.0 / max(cpu_dt, 1e-3)))
             cpu_n, cpu_dt = cpu_rollout_sample(scaled)
             args.cpu_batch = scaled
@@ -371,7 +372,7 @@ def run_cuda(args, rank, world, local_rank):
                     "steps_per_launch": gae_steps, "scan": "strict float64 sequential (bit-exact)"},
             "cpu_baseline": ({"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
                               "sample": "%d start states x %d steps (one pass, %.1f s)" % (args.cpu_batch, T - 1, cpu_dt)}
-                             if world == 1 else None),
+                             if not skip_cpu else None),
             "e2e": {"value": e2e_n / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(obs_host.nbytes), "d2h_bytes_per_step": int(d2h),
                     "api": "ModelSampler.reset/sample/finish_all_paths + ModelBuffer.get (numpy in, numpy out)"},

@@ -52,7 +52,6 @@ struct TcParams {
     float* out; long long out_member_stride;   // out[e*stride + row*Nout + c]
     int ntiles;
     int act_x2;                // packed 16-bit activation math (precision modes *_X2)
-    int role_mode;             // experiment: 1 = control warps get the highest warp ids
     int member_act[CMBPO_MAX_E];   // ACT == 0 kernels (merged nets): hidden activation per member
     unsigned long long* dbg;   // optional [grid][16] cycle counters (protocol timing aid)
 };
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     // producer.  The SM's issue arbiter prefers the highest warp id, so the control warps (whose
     // instructions gate everything else) are never starved by the 4 epilogue warps on their sub-core.
     const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int warp = p.role_mode ? (hw_warp + 4) % 20 : hw_warp;   // logical role id: 0-3 control, 4-19 epilogue
+    const int warp = hw_warp;                                  // role id: 0-3 control, 4-19 epilogue
     const int nh2 = (p.parts == 1) ? 2 : 1;                    // H2 buffers (TMEM budget)
     const uint32_t col_out = 512u - (uint32_t)(p.NP * G);      // OUT occupies the top G*NP columns
     const int NPp = p.NP / p.parts;
@@ -299,41 +298,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: warp-uniform control flow, one elected lane issues every tcgen05.mma / commit =====
-        const uint32_t idesc_h = idesc_f16(FMT, 64);
+    } else if (warp == 2) {
+        // ===== layer-2 MMA issuer: OUT(member) += H2[chunk] x W2[rows of the chunk] =====
+        // A warp of its own: the bookkeeping of a partial (three barrier waits, two commits) costs the
+        // issuing thread ~1000 cycles per chunk, which on the layer-1 issuer's instruction stream was
+        // the kernel's critical path.  The two issuers only meet in the tensor pipe.
         const uint32_t idesc_o = idesc_f16(FMT, NPp);
+        const uint64_t dW2 = smem_desc_sw128(smem_u32(sW2));
+        uint32_t s2 = 0, ph2 = 0, c1 = 0, m = 0;
+        unsigned long long c_w2 = 0, c_h2 = 0, c_out = 0;
+        for (long long u = u0; u < u1; ++u) {
+            int jin = 0;
+            for (int jj = 0; jj < NC; ++jj) {
+                const uint32_t hb = (nh2 == 2) ? (c1 & 1) : 0, hn = (nh2 == 2) ? (c1 >> 1) : c1;
+                if (jin == 0) wait_t<DBG>(bar + W2_FULL + s2, ph2, c_w2);
+                if (jj == 0) wait_t<DBG>(bar + OUT_EMPTY, (m & 1) ^ 1, c_out);
+                wait_t<DBG>(bar + H2_FULL + hb, hn & 1, c_h2);
+                tc_fence_after();
+                const bool last_in_slot = (jin == p.cps - 1) || (jj == NC - 1);
+                if (elect_one()) {
+                    for (int q = 0; q < p.parts; ++q) {
+                        const uint64_t dB = dW2 + (uint64_t)((s2 * W2SLOT + (jin * p.parts + q) * NPp * 128) >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_f16_ts(tmem + col_out + (jj / CPM) * p.NP + q * NPp, tmem + COL_H2 + hb * 32 + ks * 8,
+                                       dB + 2 * ks, idesc_o, !(jj % CPM == 0 && ks == 0));
+                    }
+                    mma_commit(bar + H2_EMPTY + hb);
+                    if (last_in_slot) mma_commit(bar + W2_EMPTY + s2);
+                    if (jj == NC - 1) mma_commit(bar + OUT_FULL);
+                }
+                __syncwarp();
+                if (last_in_slot) { jin = 0; if (++s2 == NS2) { s2 = 0; ph2 ^= 1; } } else ++jin;
+                ++c1;
+            }
+            ++m;
+        }
+        if (DBG && p.dbg && lane == 0) {
+            unsigned long long* d = p.dbg + blockIdx.x * 16;
+            d[6] = c_h2; d[7] = c_out; d[11] = c_w2;
+        }
+    } else if (warp == 1) {
+        // ===== layer-0/1 MMA issuer: warp-uniform control flow, one elected lane issues every tcgen05.mma / commit =====
+        const uint32_t idesc_h = idesc_f16(FMT, 64);
         const uint64_t dXA = smem_desc_sw128(smem_u32(sXA));
         const uint64_t dW0 = smem_desc_sw128(smem_u32(sW));
-        const uint64_t dW2 = smem_desc_sw128(smem_u32(sW2));
-        uint32_t s = 0, ph = 0, s2 = 0, ph2 = 0, g = 0, m = 0, c1 = 0, it = 0;
-        unsigned long long c_w = 0, c_d = 0, c_h1 = 0, c_h2 = 0, c_out = 0, c_x = 0;
+        uint32_t s = 0, ph = 0, g = 0, m = 0, it = 0;
+        unsigned long long c_w = 0, c_d = 0, c_h1 = 0, c_x = 0;
         const long long t_begin = DBG ? clock64() : 0;
         auto next_stage = [&]() { if (++s == NSM) { s = 0; ph ^= 1; } };
-        auto l2_partial = [&](int jj) {             // OUT += H2[chunk jj] x W2[rows of chunk jj]
-            const uint32_t hb = (nh2 == 2) ? (c1 & 1) : 0, hn = (nh2 == 2) ? (c1 >> 1) : c1;
-            const int jin = jj % p.cps;
-            if (jin == 0) wait_t<DBG>(bar + W2_FULL + s2, ph2, c_w);
-            if (jj == 0) wait_t<DBG>(bar + OUT_EMPTY, (m & 1) ^ 1, c_out);
-            wait_t<DBG>(bar + H2_FULL + hb, hn & 1, c_h2);
-            tc_fence_after();
-            TRACE(0, 700 + jj);
-            const bool last_in_slot = (jin == p.cps - 1) || (jj == NC - 1);
-            if (elect_one()) {
-                for (int q = 0; q < p.parts; ++q) {
-                    const uint64_t dB = dW2 + (uint64_t)((s2 * W2SLOT + (jin * p.parts + q) * NPp * 128) >> 4);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        mma_f16_ts(tmem + col_out + (jj / CPM) * p.NP + q * NPp, tmem + COL_H2 + hb * 32 + ks * 8,
-                                   dB + 2 * ks, idesc_o, !(jj % CPM == 0 && ks == 0));
-                }
-                mma_commit(bar + H2_EMPTY + hb);
-                if (last_in_slot) mma_commit(bar + W2_EMPTY + s2);
-            }
-            __syncwarp();
-            if (last_in_slot) { if (++s2 == NS2) { s2 = 0; ph2 ^= 1; } }
-            ++c1;
-        };
         int cur_tile = -1;
         for (long long u = u0; u < u1; ++u) {
             const int tile = (int)(u / n_groups);
@@ -393,20 +406,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     }
                     ++g;
                     TRACE(0, 400 + j);
-                    if (j >= 1) l2_partial(j - 1);
-                    TRACE(0, 500 + j);
                 }
-                l2_partial(NC - 1);
-                if (elect_one()) mma_commit(bar + OUT_FULL);
-                __syncwarp();
-                TRACE(0, 600);
                 ++m;
             }
         }
         if (DBG && p.dbg && lane == 0) {
             unsigned long long* d = p.dbg + blockIdx.x * 16;
             d[2] = (unsigned long long)(clock64() - t_begin);
-            d[3] = c_w; d[4] = c_d; d[5] = c_h1; d[6] = c_h2; d[7] = c_out; d[8] = c_x;
+            d[3] = c_w; d[4] = c_d; d[5] = c_h1; d[8] = c_x;
         }
     }
     } else {
@@ -769,7 +776,6 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     p.act_x2 = act_x2;
     for (int i = 0; i < CMBPO_MAX_E; ++i) p.member_act[i] = net.member_act[i];
     const int act_sel = net.member_act[0] >= 0 ? 0 : net.acts[0];
-    { static const char* rm = getenv("CMBPO_TC_ROLES"); p.role_mode = rm ? atoi(rm) : 0; }
     static const char* dbg_env = getenv("CMBPO_TC_DEBUG");
     const bool dbg_big = dbg_env && atoi(dbg_env) == 1 && HD == 512 && group == 1 && net.acts[0] == CMBPO_ACT_SWISH;
     const bool dbg_grp = dbg_env && atoi(dbg_env) == 2 && group == 4 && act_sel == 0;
@@ -786,7 +792,7 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         const char* names[14] = {"prod_total", "prod_wait_wempty", "mma_total", "mma_wait_wfull", "mma_wait_dempty",
                                  "mma_wait_h1", "mma_wait_h2full", "mma_wait_outempty", "mma_wait_x", "epi_total",
-                                 "epi_wait_dfull", "-", "epi_drain", "epi_wait_outfull"};
+                                 "epi_wait_dfull", "l2_wait_w2full", "epi_drain", "epi_wait_outfull"};
         for (int k = 0; k < 14; ++k) {
             double sum = 0; int n = 0;
             for (int b = 0; b < ctx->sm_count && b < p.ntiles; ++b) { sum += (double)h[(size_t)b * 16 + k]; ++n; }
