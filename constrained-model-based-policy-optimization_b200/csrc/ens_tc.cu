@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         }
     } else if (warp == 1) {
         // ===== layer-0/1 MMA issuer: warp-uniform control flow, one elected lane issues every tcgen05.mma / commit =====
-        const uint32_t idesc_h = idesc_f16(FMT, 64);
+        const uint32_t idesc_h = idesc_f16(FMT, 64), idesc_h2 = idesc_f16(FMT, 128);
         const uint64_t dXA = smem_desc_sw128(smem_u32(sXA));
         const uint64_t dW0 = smem_desc_sw128(smem_u32(sW));
         uint32_t s = 0, ph = 0, g = 0, m = 0, it = 0;
@@ -360,20 +360,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 for (int j0 = 0; j0 < NC; j0 += G0) {       // layer 0: D = XA x W0 chunk (G0 chunks per stage)
                     wait_t<DBG>(bar + W_FULL + s, ph, c_w);
 #pragma unroll
-                    for (int jj = 0; jj < G0; ++jj) {
-                        const uint32_t buf = g & 1, n = g >> 1;
-                        wait_t<DBG>(bar + D_EMPTY + buf, (n & 1) ^ 1, c_d);
+                    for (int jj = 0; jj < G0; jj += 2) {
+                        // two chunks per instruction (N = 128 fills both accumulator buffers; their
+                        // tiles are adjacent in the stage): halves this thread's per-chunk bookkeeping,
+                        // which paces the drain-bound layer-0 phase
+                        const uint32_t n = g >> 1;                  // g is even here
+                        wait_t<DBG>(bar + D_EMPTY + 0, (n & 1) ^ 1, c_d);
+                        wait_t<DBG>(bar + D_EMPTY + 1, (n & 1) ^ 1, c_d);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t dB = dW0 + (uint64_t)((s * STAGE + jj * TILE) >> 4);
                             for (int ks = 0; ks < p.KS0; ++ks)
-                                mma_f16(tmem + COL_D + buf * 64, dXA + 2 * ks, dB + 2 * ks, idesc_h, ks > 0);
-                            mma_commit(bar + D_FULL + buf);
-                            if (jj == G0 - 1) mma_commit(bar + W_EMPTY + s);
+                                mma_f16(tmem + COL_D, dXA + 2 * ks, dB + 2 * ks, idesc_h2, ks > 0);
+                            mma_commit(bar + D_FULL + 0);
+                            mma_commit(bar + D_FULL + 1);
+                            if (jj == G0 - 2) mma_commit(bar + W_EMPTY + s);
                         }
                         __syncwarp();
                         TRACE(0, 100 + j0 + jj);
-                        ++g;
+                        g += 2;
                     }
                     next_stage();
                 }

@@ -170,80 +170,128 @@ struct StepArgs {
     cmbpo_rollout_bufs b;
 };
 
+// One block iteration handles STEP_ROWS paths in three phases, so that every phase runs dense:
+//   0: one thread per path  -- elite member (Philox or injected), alive mask
+//   1: one thread per (path, obs dim) -- member statistics, KL, next state (row_math.cuh)
+//   2: one thread per path  -- ordered reductions over the dims, statics, sampler rules, the
+//                              per-step scalars of ModelBuffer (coalesced: time-major rows)
+//   3: one thread per (path, dim) -- obs / next_obs / act / mu rows, carried state
+// (With phase 2 executed by the dim-0 thread of each path, as FakeEnv.step still does, a warp
+// holds two paths and the serial part runs at 2/32 lane utilisation: 3x the instructions.)
+constexpr int STEP_ROWS = 64;
+
+__host__ __device__ inline size_t step_smem_bytes(int O) {
+    return (size_t)STEP_ROWS * O * (3 * sizeof(float) + 1) + STEP_ROWS * (sizeof(int) + 1) + 16;
+}
+
 __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a) {
-    __shared__ RowShared sh;
-    const int O = a.O, A = a.A, t = a.t, RB = ROW_THREADS / O;
-    const int rb = threadIdx.x / O, dim = threadIdx.x - rb * O;
-    if (threadIdx.x < 4) sh.stats[threadIdx.x] = 0.0;
-    __syncthreads();
-    for (int64_t base = (int64_t)blockIdx.x * RB; base < a.B; base += (int64_t)gridDim.x * RB) {
-        const int64_t p = base + rb;
-        const bool active = rb < RB && p < a.B && a.alive[p];
-        int member = 0;
-        float obs_d = 0.f;
-        if (active) {
-            const int64_t gid = a.path_base + p;
-            const int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, gid, t, a.n_elite);
-            member = a.c.elite[pos];
-            float eps = 1.0f;
-            if (!a.c.deterministic)
-                eps = a.state_eps ? a.state_eps[p * O + dim] : philox_normal(a.seed, gid, t, RNG_STREAM_STATE, dim);
-            obs_d = a.cur_obs[p * O + dim];
-            RawDyn raw(a.raw, a.B, 2 * a.c.D, p);
-            EnvDimOut d = env_dim(a.c, raw, dim, member, obs_d, eps);
-            sh.kl[threadIdx.x] = d.kl; sh.epv[threadIdx.x] = d.epv; sh.nx[threadIdx.x] = d.nx;
-            sh.fin[threadIdx.x] = isfinite(d.nx) ? 1 : 0;
+    extern __shared__ __align__(16) unsigned char step_smem[];
+    const int O = a.O, A = a.A, t = a.t, NI = STEP_ROWS * O;
+    float* s_kl = reinterpret_cast<float*>(step_smem);
+    float* s_epv = s_kl + NI;
+    float* s_nx = s_epv + NI;
+    int* s_member = reinterpret_cast<int*>(s_nx + NI);
+    unsigned char* s_fin = reinterpret_cast<unsigned char*>(s_member + STEP_ROWS);
+    unsigned char* s_state = s_fin + NI;             // 0 = not fed, 1 = stored, 2 = cut
+    __shared__ double s_stats[4];
+    double st0 = 0.0, st1 = 0.0, st2 = 0.0, st3 = 0.0;   // rows fed, sum dkl, rows stored, sum ep_var
+    if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
+    for (int64_t base = (int64_t)blockIdx.x * STEP_ROWS; base < a.B; base += (int64_t)gridDim.x * STEP_ROWS) {
+        if (threadIdx.x < STEP_ROWS) {
+            const int64_t p = base + threadIdx.x;
+            int member = -1;
+            if (p < a.B && a.alive[p]) {
+                const int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, a.path_base + p, t, a.n_elite);
+                member = a.c.elite[pos];
+            }
+            s_member[threadIdx.x] = member;
+            s_state[threadIdx.x] = 0;
         }
         __syncthreads();
-        if (active && dim == 0) {
+        for (int idx = threadIdx.x; idx < NI; idx += ROW_THREADS) {
+            const int r = idx / O, dim = idx - r * O;
+            const int member = s_member[r];
+            if (member < 0) continue;
+            const int64_t p = base + r;
+            float eps = 1.0f;
+            if (!a.c.deterministic)
+                eps = a.state_eps ? a.state_eps[p * O + dim]
+                                  : philox_normal(a.seed, a.path_base + p, t, RNG_STREAM_STATE, dim);
             RawDyn raw(a.raw, a.B, 2 * a.c.D, p);
-            EnvRowOut r = env_row_finish(a.c, raw, member, sh.kl + rb * O, sh.epv + rb * O, sh.nx + rb * O,
-                                         sh.fin + rb * O);
+            const EnvDimOut d = env_dim(a.c, raw, dim, member, a.cur_obs[p * O + dim], eps);
+            s_kl[idx] = d.kl; s_epv[idx] = d.epv; s_nx[idx] = d.nx;
+            s_fin[idx] = isfinite(d.nx) ? 1 : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x < STEP_ROWS && s_member[threadIdx.x] >= 0) {
+            const int r = threadIdx.x;
+            const int64_t p = base + r;
+            RawDyn raw(a.raw, a.B, 2 * a.c.D, p);
+            const EnvRowOut o = env_row_finish(a.c, raw, s_member[r], s_kl + r * O, s_epv + r * O, s_nx + r * O,
+                                               s_fin + r * O);
             const float v = a.v[p], vc = a.vc[p];
             // uncertainty cut-off BEFORE the step is stored (model_sampler.py:275-290)
-            const double next_dkl = a.b.cum_dkl[p] + (double)r.dkl_path;
+            const double next_dkl = a.b.cum_dkl[p] + (double)o.dkl_path;
             const bool cut = a.uncertainty && next_dkl >= a.dkl_lim;
-            sh.cut[rb] = cut ? 1 : 0;
-            atomicAdd(&sh.stats[0], 1.0); atomicAdd(&sh.stats[1], (double)r.dkl_path);
+            st0 += 1.0; st1 += (double)o.dkl_path;
             if (cut) {
+                s_state[r] = 2;
                 a.alive[p] = 0;
                 a.b.end_reason[p] = CMBPO_END_UNCERTAIN;
                 a.b.last_val[p] = v; a.b.last_cval[p] = vc;      // V(s_t), VC(s_t): model_sampler.py:401-407
             } else {
+                s_state[r] = 1;
                 const int64_t row = (int64_t)t * a.B + p;          // ModelBuffer.store_multiple, time-major
-                a.b.rew[row] = r.rew; a.b.val[row] = v; a.b.cost[row] = r.cost; a.b.cval[row] = vc;
-                a.b.logp[row] = a.logp[p]; a.b.dyn_error[row] = r.ep_var_mean; a.b.dkl[row] = r.dkl_path;
-                a.b.term[row] = r.term ? 1 : 0;
+                a.b.rew[row] = o.rew; a.b.val[row] = v; a.b.cost[row] = o.cost; a.b.cval[row] = vc;
+                a.b.logp[row] = a.logp[p]; a.b.dyn_error[row] = o.ep_var_mean; a.b.dkl[row] = o.dkl_path;
+                a.b.term[row] = o.term ? 1 : 0;
                 a.b.length[p] = t + 1;
                 a.b.cum_dkl[p] = next_dkl;                        // model_sampler.py:332
-                a.b.path_return[p] += (double)r.rew;              // :317-318
-                a.b.path_cost[p] += (double)r.cost;
-                atomicAdd(&sh.stats[2], 1.0); atomicAdd(&sh.stats[3], (double)r.ep_var_sum);
+                a.b.path_return[p] += (double)o.rew;              // :317-318
+                a.b.path_cost[p] += (double)o.cost;
+                st2 += 1.0; st3 += (double)o.ep_var_sum;
                 if (t >= a.last_storable) {                       // path_length >= max_path_length-1 (:352)
                     a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_HORIZON; a.pending[p] = 3;
-                } else if (r.term) {                              // env terminal (:357-364)
+                } else if (o.term) {                              // env terminal (:357-364)
                     a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_TERMINAL;
                     a.b.last_val[p] = 0.f; a.pending[p] = 2;
                 }
             }
         }
         __syncthreads();
-        if (active && !sh.cut[rb]) {
-            const int64_t row = (int64_t)t * a.B + p;
-            const float nx = sh.nx[threadIdx.x];
-            a.b.obs[row * O + dim] = obs_d;
+        for (int idx = threadIdx.x; idx < NI; idx += ROW_THREADS) {
+            const int r = idx / O, dim = idx - r * O;
+            if (s_state[r] != 1) continue;
+            const int64_t p = base + r, row = (int64_t)t * a.B + p;
+            const float nx = s_nx[idx];
+            a.b.obs[row * O + dim] = a.cur_obs[p * O + dim];
             a.b.nextobs[row * O + dim] = nx;
             a.cur_obs[p * O + dim] = nx;                          // model_sampler.py:350
-            for (int i = dim; i < A; i += O) {
-                a.b.act[row * A + i] = a.pi[p * A + i];
-                a.b.mu[row * A + i] = a.mu[p * A + i];
-            }
+        }
+        for (int idx = threadIdx.x; idx < STEP_ROWS * A; idx += ROW_THREADS) {
+            const int r = idx / A, i = idx - r * A;
+            if (s_state[r] != 1) continue;
+            const int64_t p = base + r, row = (int64_t)t * a.B + p;
+            a.b.act[row * A + i] = a.pi[p * A + i];
+            a.b.mu[row * A + i] = a.mu[p * A + i];
         }
         __syncthreads();
     }
-    // per-step statistics: rows fed, sum dkl, rows stored, sum ep_var
-    if (threadIdx.x < 4 && sh.stats[threadIdx.x] != 0.0)
-        atomicAdd(a.b.step_stats + (int64_t)a.t * 4 + threadIdx.x, sh.stats[threadIdx.x]);
+    // per-step statistics: warp-reduce the row threads' partial sums, one shared atomic per warp
+    if (threadIdx.x < STEP_ROWS) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            st0 += __shfl_down_sync(0xffffffffu, st0, off); st1 += __shfl_down_sync(0xffffffffu, st1, off);
+            st2 += __shfl_down_sync(0xffffffffu, st2, off); st3 += __shfl_down_sync(0xffffffffu, st3, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_stats[0], st0); atomicAdd(&s_stats[1], st1);
+            atomicAdd(&s_stats[2], st2); atomicAdd(&s_stats[3], st3);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_stats[threadIdx.x] != 0.0)
+        atomicAdd(a.b.step_stats + (int64_t)a.t * 4 + threadIdx.x, s_stats[threadIdx.x]);
 }
 
 __global__ void rollout_init_kernel(int64_t B, int O, const float* start, float* cur, uint8_t* alive,
@@ -446,8 +494,14 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
         sa.state_eps = bufs->state_eps ? bufs->state_eps + (size_t)t * B * O : nullptr;
         sa.b = *bufs;
         {
+            static bool smem_set = false;
+            if (!smem_set) {
+                CUDA_TRY(cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)step_smem_bytes(CMBPO_MAX_OBS)));
+                smem_set = true;
+            }
             ProfScope prof(ctx, CMBPO_PROF_STEP);
-            rollout_step_kernel<<<min(cdiv(B, ROW_THREADS / O), ctx->sm_count * 16), ROW_THREADS, 0, ctx->stream>>>(sa);
+            rollout_step_kernel<<<(unsigned)std::min<int64_t>(cdiv(B, STEP_ROWS), (int64_t)ctx->sm_count * 4), ROW_THREADS, step_smem_bytes(O), ctx->stream>>>(sa);
         }
         ctx->launches++;
     }
