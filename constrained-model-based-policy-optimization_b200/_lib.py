@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcmbpo_b200.so")
+# CMBPO_B200_LIB: developer override to A/B two builds of the same ABI on one GPU box
+LIB_PATH = os.environ.get("CMBPO_B200_LIB") or os.path.join(_HERE, "libcmbpo_b200.so")
 
 # enums of include/cmbpo_b200.h
 NET_DYN, NET_V, NET_VC, NET_ACTOR = 0, 1, 2, 3

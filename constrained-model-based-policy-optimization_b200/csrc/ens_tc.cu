@@ -339,7 +339,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             d[6] = c_h2; d[7] = c_out; d[11] = c_w2;
         }
     } else if (warp == 1) {
-        // ===== layer-0/1 MMA issuer: warp-uniform control flow, one elected lane issues every tcgen05.mma / commit =====
+        // ===== layer-0/1 MMA issuer.  Wide members (G == 1): ONE elected thread runs the whole loop, waits
+        // included, so that no warp-level election / reconvergence sits between two batches of MMAs
+        // (-6% on the 512-wide ensemble).  Grouped narrow members have short batches and are paced by
+        // the drains; there the warp-uniform loop with a per-batch election measured 5% faster. =====
+        constexpr bool SINGLE = (G == 1);
         const uint32_t idesc_h = idesc_f16(FMT, 64), idesc_h2 = idesc_f16(FMT, 128);
         const uint64_t dXA = smem_desc_sw128(smem_u32(sXA));
         const uint64_t dW0 = smem_desc_sw128(smem_u32(sW));
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         unsigned long long c_w = 0, c_d = 0, c_h1 = 0, c_x = 0;
         const long long t_begin = DBG ? clock64() : 0;
         auto next_stage = [&]() { if (++s == NSM) { s = 0; ph ^= 1; } };
+        if (!SINGLE || elect_one()) {
         int cur_tile = -1;
         for (long long u = u0; u < u1; ++u) {
             const int tile = (int)(u / n_groups);
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                         wait_t<DBG>(bar + D_EMPTY + 0, (n & 1) ^ 1, c_d);
                         wait_t<DBG>(bar + D_EMPTY + 1, (n & 1) ^ 1, c_d);
                         tc_fence_after();
-                        if (elect_one()) {
+                        if (SINGLE || elect_one()) {
                             const uint64_t dB = dW0 + (uint64_t)((s * STAGE + jj * TILE) >> 4);
                             for (int ks = 0; ks < p.KS0; ++ks)
                                 mma_f16(tmem + COL_D, dXA + 2 * ks, dB + 2 * ks, idesc_h2, ks > 0);
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                             mma_commit(bar + D_FULL + 1);
                             if (jj == G0 - 2) mma_commit(bar + W_EMPTY + s);
                         }
-                        __syncwarp();
+                        if (!SINGLE) __syncwarp();
                         TRACE(0, 100 + j0 + jj);
                         g += 2;
                     }
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     for (int kq = 0; kq < KP / TPS; ++kq) {
                         wait_t<DBG>(bar + W_FULL + s, ph, c_w);
                         tc_fence_after();
-                        if (elect_one()) {
+                        if (SINGLE || elect_one()) {
 #pragma unroll
                             for (int tt = 0; tt < TPS; ++tt) {
                                 const uint64_t dB = dW0 + (uint64_t)((s * STAGE + tt * TILE) >> 4);
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                             mma_commit(bar + W_EMPTY + s);
                             if (kq == KP / TPS - 1) mma_commit(bar + D_FULL + buf);
                         }
-                        __syncwarp();
+                        if (!SINGLE) __syncwarp();
                         next_stage();
                     }
                     ++g;
@@ -415,6 +420,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 ++m;
             }
         }
+        }
+        __syncwarp();
         if (DBG && p.dbg && lane == 0) {
             unsigned long long* d = p.dbg + blockIdx.x * 16;
             d[2] = (unsigned long long)(clock64() - t_begin);
@@ -799,9 +806,12 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
                                  "mma_wait_h1", "mma_wait_h2full", "mma_wait_outempty", "mma_wait_x", "epi_total",
                                  "epi_wait_dfull", "l2_wait_w2full", "epi_drain", "epi_wait_outfull"};
         for (int k = 0; k < 14; ++k) {
-            double sum = 0; int n = 0;
-            for (int b = 0; b < ctx->sm_count && b < p.ntiles; ++b) { sum += (double)h[(size_t)b * 16 + k]; ++n; }
-            fprintf(stderr, "tcdbg %-18s %12.0f cycles/CTA\n", names[k], sum / (n ? n : 1));
+            double sum = 0, lo = 1e30, hi = 0; int n = 0;
+            for (int b = 0; b < ctx->sm_count && b < p.ntiles; ++b) {
+                const double v = (double)h[(size_t)b * 16 + k];
+                sum += v; lo = v < lo ? v : lo; hi = v > hi ? v : hi; ++n;
+            }
+            fprintf(stderr, "tcdbg %-18s %12.0f cycles/CTA (min %.0f, max %.0f)\n", names[k], sum / (n ? n : 1), lo, hi);
         }
         static int printed = 0;
         if (!printed++) {
