@@ -396,8 +396,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     tc_fence_after();
                     TRACE(0, 300 + j);
                     for (int kq = 0; kq < KP / TPS; ++kq) {
-                        wait_t<DBG>(bar + W_FULL + s, ph, c_w);
-                        tc_fence_after();
+                        wait_t<DBG>(bar + W_FULL + s, ph, c_w);      // TMA completion: no tcgen05 fence needed
                         if (SINGLE || elect_one()) {
 #pragma unroll
                             for (int tt = 0; tt < TPS; ++tt) {

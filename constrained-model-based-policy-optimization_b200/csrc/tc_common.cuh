@@ -49,6 +49,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+    // rolled: ptxas unrolls this loop 64x otherwise (2 KB of code per wait site, ~40 KB per kernel)
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
