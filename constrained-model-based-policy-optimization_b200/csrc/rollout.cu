@@ -87,6 +87,16 @@ struct RawDyn {             // raw outputs [E, N, W]: row pointer of member 0 + 
     const float* row0; int64_t estride;
     __device__ RawDyn(const float* raw, int64_t N, int W, int64_t p) : row0(raw + p * W), estride(N * (int64_t)W) {}
     __device__ float operator()(int e, int c) const { return __ldg(row0 + (int64_t)e * estride + c); }
+    __device__ const float* ptr(int c) const { return row0 + c; }      // member 0; member e at + e * estride
+    __device__ static float load(const float* q) { return __ldg(q); }
+};
+
+struct RawStaged {          // the same rows staged in shared memory: [E, rows, W]
+    const float* row0; int estride;
+    __device__ RawStaged(const float* s_raw, int rows, int W, int r) : row0(s_raw + r * W), estride(rows * W) {}
+    __device__ float operator()(int e, int c) const { return row0[e * estride + c]; }
+    __device__ const float* ptr(int c) const { return row0 + c; }
+    __device__ static float load(const float* q) { return *q; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -170,34 +180,53 @@ struct StepArgs {
     cmbpo_rollout_bufs b;
 };
 
-// One block iteration handles STEP_ROWS paths in three phases, so that every phase runs dense:
-//   0: one thread per path  -- elite member (Philox or injected), alive mask
+// One block iteration handles `rows` = floor(512 / O) consecutive paths in phases that all run dense:
+//   0: warp e stages member e's raw outputs [rows, 2D] (contiguous in global memory) into shared
+//      memory with batches of 8 independent 8-byte loads per lane, so the DRAM / L2 latency is paid
+//      twice per block instead of once per member and dimension; one thread per path draws the
+//      elite member (Philox or injected)
 //   1: one thread per (path, obs dim) -- member statistics, KL, next state (row_math.cuh)
 //   2: one thread per path  -- ordered reductions over the dims, statics, sampler rules, the
 //                              per-step scalars of ModelBuffer (coalesced: time-major rows)
 //   3: one thread per (path, dim) -- obs / next_obs / act / mu rows, carried state
 // (With phase 2 executed by the dim-0 thread of each path, as FakeEnv.step still does, a warp
-// holds two paths and the serial part runs at 2/32 lane utilisation: 3x the instructions.)
-constexpr int STEP_ROWS = 64;
-
-__host__ __device__ inline size_t step_smem_bytes(int O) {
-    return (size_t)STEP_ROWS * O * (3 * sizeof(float) + 1) + STEP_ROWS * (sizeof(int) + 1) + 16;
+// holds two paths and the serial part runs at 2/32 lane utilisation.)
+__host__ __device__ inline int step_rows(int O) { return 512 / O < 64 ? 512 / O : 64; }
+__host__ __device__ inline size_t step_smem_bytes(int O, int E, int W) {
+    const size_t rows = step_rows(O);
+    return (size_t)E * rows * W * 4 + rows * O * (3 * sizeof(float) + 1) + rows * (sizeof(int) + 1) + 16;
 }
 
 __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a) {
     extern __shared__ __align__(16) unsigned char step_smem[];
-    const int O = a.O, A = a.A, t = a.t, NI = STEP_ROWS * O;
-    float* s_kl = reinterpret_cast<float*>(step_smem);
+    const int O = a.O, A = a.A, t = a.t, E = a.c.E, W = 2 * a.c.D;
+    const int rows = step_rows(O), NI = rows * O;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_raw = reinterpret_cast<float*>(step_smem);
+    float* s_kl = s_raw + E * rows * W;
     float* s_epv = s_kl + NI;
     float* s_nx = s_epv + NI;
     int* s_member = reinterpret_cast<int*>(s_nx + NI);
-    unsigned char* s_fin = reinterpret_cast<unsigned char*>(s_member + STEP_ROWS);
+    unsigned char* s_fin = reinterpret_cast<unsigned char*>(s_member + rows);
     unsigned char* s_state = s_fin + NI;             // 0 = not fed, 1 = stored, 2 = cut
     __shared__ double s_stats[4];
     double st0 = 0.0, st1 = 0.0, st2 = 0.0, st3 = 0.0;   // rows fed, sum dkl, rows stored, sum ep_var
     if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
-    for (int64_t base = (int64_t)blockIdx.x * STEP_ROWS; base < a.B; base += (int64_t)gridDim.x * STEP_ROWS) {
-        if (threadIdx.x < STEP_ROWS) {
+    for (int64_t base = (int64_t)blockIdx.x * rows; base < a.B; base += (int64_t)gridDim.x * rows) {
+        const int nrows = (a.B - base) < rows ? (int)(a.B - base) : rows;
+        const int n2 = nrows * W / 2;                // W is even: 8-byte units, always aligned
+        for (int e = warp; e < E; e += ROW_THREADS / 32) {
+            const float2* src = reinterpret_cast<const float2*>(a.raw + ((int64_t)e * a.B + base) * W);
+            float2* dst = reinterpret_cast<float2*>(s_raw + e * rows * W);
+            for (int i0 = lane; i0 < n2; i0 += 32 * 8) {
+                float2 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (i0 + 32 * k < n2) v[k] = __ldg(src + i0 + 32 * k);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (i0 + 32 * k < n2) dst[i0 + 32 * k] = v[k];
+            }
+        }
+        if (threadIdx.x < rows) {
             const int64_t p = base + threadIdx.x;
             int member = -1;
             if (p < a.B && a.alive[p]) {
@@ -217,16 +246,16 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
             if (!a.c.deterministic)
                 eps = a.state_eps ? a.state_eps[p * O + dim]
                                   : philox_normal(a.seed, a.path_base + p, t, RNG_STREAM_STATE, dim);
-            RawDyn raw(a.raw, a.B, 2 * a.c.D, p);
+            RawStaged raw(s_raw, rows, W, r);
             const EnvDimOut d = env_dim(a.c, raw, dim, member, a.cur_obs[p * O + dim], eps);
             s_kl[idx] = d.kl; s_epv[idx] = d.epv; s_nx[idx] = d.nx;
             s_fin[idx] = isfinite(d.nx) ? 1 : 0;
         }
         __syncthreads();
-        if (threadIdx.x < STEP_ROWS && s_member[threadIdx.x] >= 0) {
+        if (threadIdx.x < rows && s_member[threadIdx.x] >= 0) {
             const int r = threadIdx.x;
             const int64_t p = base + r;
-            RawDyn raw(a.raw, a.B, 2 * a.c.D, p);
+            RawStaged raw(s_raw, rows, W, r);
             const EnvRowOut o = env_row_finish(a.c, raw, s_member[r], s_kl + r * O, s_epv + r * O, s_nx + r * O,
                                                s_fin + r * O);
             const float v = a.v[p], vc = a.vc[p];
@@ -268,7 +297,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
             a.b.nextobs[row * O + dim] = nx;
             a.cur_obs[p * O + dim] = nx;                          // model_sampler.py:350
         }
-        for (int idx = threadIdx.x; idx < STEP_ROWS * A; idx += ROW_THREADS) {
+        for (int idx = threadIdx.x; idx < rows * A; idx += ROW_THREADS) {
             const int r = idx / A, i = idx - r * A;
             if (s_state[r] != 1) continue;
             const int64_t p = base + r, row = (int64_t)t * a.B + p;
@@ -278,13 +307,13 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
         __syncthreads();
     }
     // per-step statistics: warp-reduce the row threads' partial sums, one shared atomic per warp
-    if (threadIdx.x < STEP_ROWS) {
+    if (threadIdx.x < 64) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             st0 += __shfl_down_sync(0xffffffffu, st0, off); st1 += __shfl_down_sync(0xffffffffu, st1, off);
             st2 += __shfl_down_sync(0xffffffffu, st2, off); st3 += __shfl_down_sync(0xffffffffu, st3, off);
         }
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             atomicAdd(&s_stats[0], st0); atomicAdd(&s_stats[1], st1);
             atomicAdd(&s_stats[2], st2); atomicAdd(&s_stats[3], st3);
         }
@@ -494,14 +523,15 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
         sa.state_eps = bufs->state_eps ? bufs->state_eps + (size_t)t * B * O : nullptr;
         sa.b = *bufs;
         {
-            static bool smem_set = false;
-            if (!smem_set) {
-                CUDA_TRY(cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)step_smem_bytes(CMBPO_MAX_OBS)));
-                smem_set = true;
+            const size_t smem = step_smem_bytes(O, dyn.E, 2 * dyn.D);
+            static size_t smem_max = 0;
+            if (smem > smem_max) {
+                CMBPO_CHECK(smem <= 200 * 1024, "rollout step: obs dim / ensemble too large for the staging buffer");
+                CUDA_TRY(cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smem_max = smem;
             }
             ProfScope prof(ctx, CMBPO_PROF_STEP);
-            rollout_step_kernel<<<(unsigned)std::min<int64_t>(cdiv(B, STEP_ROWS), (int64_t)ctx->sm_count * 4), ROW_THREADS, step_smem_bytes(O), ctx->stream>>>(sa);
+            rollout_step_kernel<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), ROW_THREADS, smem, ctx->stream>>>(sa);
         }
         ctx->launches++;
     }

@@ -167,11 +167,16 @@ __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int 
     float nd[EMAX], ls[EMAX], vr[EMAX], rv[EMAX];
     const float sg = c.sig_out[o], mu = c.mu_out[o], l2s = c.l2s_out[o];
     float sel = 0.f;
+    // two running pointers (mean column, log-variance column) advanced by the member stride
+    const float* pm = raw.ptr(o);
+    const float* pv = raw.ptr(c.D + o);
+    const auto es = raw.estride;
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) {
         if (e < E) {
-            const float mean = __fadd_rn(__fmul_rn(sg, raw(e, o)), mu);          // pe.py:815-821
-            const float logvar = __fadd_rn(l2s, raw(e, c.D + o));                // pe.py:826-828
+            const float mean = __fadd_rn(__fmul_rn(sg, raw.load(pm)), mu);        // pe.py:815-821
+            const float logvar = __fadd_rn(l2s, raw.load(pv));                    // pe.py:826-828
+            pm += es; pv += es;
             const float var = __expf(logvar);                                    // pe.py:833
             float x = mean;
             if (!c.deterministic) x = __fadd_rn(mean, __fmul_rn(sqrtf(var), eps));   // fake_env.py:104-106
