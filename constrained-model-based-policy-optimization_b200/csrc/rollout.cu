@@ -191,13 +191,14 @@ struct StepArgs {
 //   3: one thread per (path, dim) -- obs / next_obs / act / mu rows, carried state
 // (With phase 2 executed by the dim-0 thread of each path, as FakeEnv.step still does, a warp
 // holds two paths and the serial part runs at 2/32 lane utilisation.)
-__host__ __device__ inline int step_rows(int O) { return 512 / O < 64 ? 512 / O : 64; }
+constexpr int STEP_THREADS = 256;     // (128-thread blocks, 8 per SM, measured the same)
+__host__ __device__ inline int step_rows(int O) { return 2 * STEP_THREADS / O < 64 ? 2 * STEP_THREADS / O : 64; }
 __host__ __device__ inline size_t step_smem_bytes(int O, int E, int W) {
     const size_t rows = step_rows(O);
     return (size_t)E * rows * W * 4 + rows * O * (3 * sizeof(float) + 1) + rows * (sizeof(int) + 1) + 16;
 }
 
-__global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a) {
+__global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs a) {
     extern __shared__ __align__(16) unsigned char step_smem[];
     const int O = a.O, A = a.A, t = a.t, E = a.c.E, W = 2 * a.c.D;
     const int rows = step_rows(O), NI = rows * O;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
     for (int64_t base = (int64_t)blockIdx.x * rows; base < a.B; base += (int64_t)gridDim.x * rows) {
         const int nrows = (a.B - base) < rows ? (int)(a.B - base) : rows;
         const int n2 = nrows * W / 2;                // W is even: 8-byte units, always aligned
-        for (int e = warp; e < E; e += ROW_THREADS / 32) {
+        for (int e = warp; e < E; e += STEP_THREADS / 32) {
             const float2* src = reinterpret_cast<const float2*>(a.raw + ((int64_t)e * a.B + base) * W);
             float2* dst = reinterpret_cast<float2*>(s_raw + e * rows * W);
             for (int i0 = lane; i0 < n2; i0 += 32 * 8) {
@@ -226,18 +227,23 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
                 for (int k = 0; k < 8; ++k) if (i0 + 32 * k < n2) dst[i0 + 32 * k] = v[k];
             }
         }
+        // the per-path scalars of phase 2 are fetched here, so their latency overlaps phases 0-1
+        float pf_v = 0.f, pf_vc = 0.f, pf_logp = 0.f;
+        double pf_dkl = 0.0, pf_ret = 0.0, pf_cost = 0.0;
         if (threadIdx.x < rows) {
             const int64_t p = base + threadIdx.x;
             int member = -1;
             if (p < a.B && a.alive[p]) {
                 const int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, a.path_base + p, t, a.n_elite);
                 member = a.c.elite[pos];
+                pf_v = a.v[p]; pf_vc = a.vc[p]; pf_logp = a.logp[p];
+                pf_dkl = a.b.cum_dkl[p]; pf_ret = a.b.path_return[p]; pf_cost = a.b.path_cost[p];
             }
             s_member[threadIdx.x] = member;
             s_state[threadIdx.x] = 0;
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < NI; idx += ROW_THREADS) {
+        for (int idx = threadIdx.x; idx < NI; idx += STEP_THREADS) {
             const int r = idx / O, dim = idx - r * O;
             const int member = s_member[r];
             if (member < 0) continue;
@@ -258,9 +264,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
             RawStaged raw(s_raw, rows, W, r);
             const EnvRowOut o = env_row_finish(a.c, raw, s_member[r], s_kl + r * O, s_epv + r * O, s_nx + r * O,
                                                s_fin + r * O);
-            const float v = a.v[p], vc = a.vc[p];
+            const float v = pf_v, vc = pf_vc;
             // uncertainty cut-off BEFORE the step is stored (model_sampler.py:275-290)
-            const double next_dkl = a.b.cum_dkl[p] + (double)o.dkl_path;
+            const double next_dkl = pf_dkl + (double)o.dkl_path;
             const bool cut = a.uncertainty && next_dkl >= a.dkl_lim;
             st0 += 1.0; st1 += (double)o.dkl_path;
             if (cut) {
@@ -272,12 +278,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
                 s_state[r] = 1;
                 const int64_t row = (int64_t)t * a.B + p;          // ModelBuffer.store_multiple, time-major
                 a.b.rew[row] = o.rew; a.b.val[row] = v; a.b.cost[row] = o.cost; a.b.cval[row] = vc;
-                a.b.logp[row] = a.logp[p]; a.b.dyn_error[row] = o.ep_var_mean; a.b.dkl[row] = o.dkl_path;
+                a.b.logp[row] = pf_logp; a.b.dyn_error[row] = o.ep_var_mean; a.b.dkl[row] = o.dkl_path;
                 a.b.term[row] = o.term ? 1 : 0;
                 a.b.length[p] = t + 1;
                 a.b.cum_dkl[p] = next_dkl;                        // model_sampler.py:332
-                a.b.path_return[p] += (double)o.rew;              // :317-318
-                a.b.path_cost[p] += (double)o.cost;
+                a.b.path_return[p] = pf_ret + (double)o.rew;      // :317-318
+                a.b.path_cost[p] = pf_cost + (double)o.cost;
                 st2 += 1.0; st3 += (double)o.ep_var_sum;
                 if (t >= a.last_storable) {                       // path_length >= max_path_length-1 (:352)
                     a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_HORIZON; a.pending[p] = 3;
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
             }
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < NI; idx += ROW_THREADS) {
+        for (int idx = threadIdx.x; idx < NI; idx += STEP_THREADS) {
             const int r = idx / O, dim = idx - r * O;
             if (s_state[r] != 1) continue;
             const int64_t p = base + r, row = (int64_t)t * a.B + p;
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) rollout_step_kernel(StepArgs a
             a.b.nextobs[row * O + dim] = nx;
             a.cur_obs[p * O + dim] = nx;                          // model_sampler.py:350
         }
-        for (int idx = threadIdx.x; idx < rows * A; idx += ROW_THREADS) {
+        for (int idx = threadIdx.x; idx < rows * A; idx += STEP_THREADS) {
             const int r = idx / A, i = idx - r * A;
             if (s_state[r] != 1) continue;
             const int64_t p = base + r, row = (int64_t)t * a.B + p;
@@ -531,7 +537,7 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
                 smem_max = smem;
             }
             ProfScope prof(ctx, CMBPO_PROF_STEP);
-            rollout_step_kernel<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), ROW_THREADS, smem, ctx->stream>>>(sa);
+            rollout_step_kernel<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), STEP_THREADS, smem, ctx->stream>>>(sa);
         }
         ctx->launches++;
     }
