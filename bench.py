@@ -310,7 +310,8 @@ def run_cuda(args, rank, world, local_rank):
     for _ in range(e2e_steps):
         out = e2e_pass()
         e2e_n += len(out[0])
-        d2h = sum(a.nbytes for a in out)
+        # bytes that crossed PCIe: a stride-0 axis (log_std, one row broadcast) is not copied
+        d2h = sum(int(np.prod([n for n, st in zip(a.shape, a.strides) if st != 0] or [1])) * a.itemsize for a in out)
     barrier()
     e2e_s = time.perf_counter() - t0
 

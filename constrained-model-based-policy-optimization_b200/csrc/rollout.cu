@@ -8,6 +8,7 @@
 // Reference: samplers/model_sampler.py:239-375 (sample), 377-416 (_finish_paths),
 //            models/fake_env.py:66-172, buffers/modelbuffer.py:114-135 (store_multiple),
 //            policies/cpo_policy.py:801-835.
+#include <cstring>
 #include "common.cuh"
 #include "row_math.cuh"
 
@@ -589,6 +590,63 @@ __global__ void stop_apply_kernel(cmbpo_rollout_bufs b, int64_t B, int stop_step
     if (b.length[p] > stop_step + 1) cut_path(b, B, p, stop_step + 1, CMBPO_END_STOPPED);
 }
 
+
+// Diagnostics of a finished rollout over the VALID steps (t < length[p]) in one pass: one thread per
+// path walks its steps in time order (time-major buffers: coalesced across paths), float64 sums.
+//   stats[0..4] = sum rew, cost, val, cval, dyn_error;  stats[5] = max dkl;
+//   stats[6] = max over (p, t) of the running return sum_{s<=t} rew;  stats[7] = number of steps
+__global__ void rollout_diag_kernel(cmbpo_rollout_bufs b, int64_t B, double* path_return, double* path_cost,
+                                    double* stats) {
+    double s[5] = {0, 0, 0, 0, 0}, mx_dkl = -1e300, mx_ret = -1e300, n = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < B; p += (int64_t)gridDim.x * blockDim.x) {
+        const int len = b.length[p];
+        double pr = 0, pc = 0;
+        for (int t = 0; t < len; ++t) {
+            const int64_t i = (int64_t)t * B + p;
+            const double r = (double)b.rew[i], c = (double)b.cost[i];
+            pr += r; pc += c;
+            s[2] += (double)b.val[i]; s[3] += (double)b.cval[i]; s[4] += (double)b.dyn_error[i];
+            mx_dkl = fmax(mx_dkl, (double)b.dkl[i]);
+            mx_ret = fmax(mx_ret, pr);
+        }
+        s[0] += pr; s[1] += pc; n += len;
+        path_return[p] = pr; path_cost[p] = pc;
+    }
+    __shared__ double sh[8][8];
+    double v[8] = {s[0], s[1], s[2], s[3], s[4], mx_dkl, mx_ret, n};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool is_max = (k == 5 || k == 6);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double o = __shfl_down_sync(0xffffffffu, v[k], off);
+            v[k] = is_max ? fmax(v[k], o) : v[k] + o;
+        }
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int k = threadIdx.x;
+        const bool is_max = (k == 5 || k == 6);
+        double a = sh[k][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) a = is_max ? fmax(a, sh[k][w]) : a + sh[k][w];
+        if (!is_max) atomicAdd(stats + k, a);
+        else {      // float64 max through the ordered-integer image (both signs)
+            long long ai = __double_as_longlong(a);
+            ai = ai >= 0 ? ai : (ai ^ 0x7fffffffffffffffLL);
+            atomicMax(reinterpret_cast<long long*>(stats) + k, ai);
+        }
+    }
+}
+
+__global__ void rollout_diag_finish_kernel(double* stats) {
+    const int k = 5 + threadIdx.x;             // decode the two maxima
+    if (threadIdx.x < 2) {
+        long long ai = reinterpret_cast<long long*>(stats)[k];
+        ai = ai >= 0 ? ai : (ai ^ 0x7fffffffffffffffLL);
+        stats[k] = __longlong_as_double(ai);
+    }
+}
 }  // namespace
 
 extern "C" int cmbpo_rollout_histogram(cmbpo_ctx* ctx, const int32_t* length, const uint8_t* end_reason,
@@ -601,6 +659,28 @@ extern "C" int cmbpo_rollout_histogram(cmbpo_ctx* ctx, const int32_t* length, co
     hist_kernel<<<max(1, min(ctx->sm_count * 4, cdiv(B, 256))), 256, 0, ctx->stream>>>(length, end_reason, B, T, d);
     ctx->launches++;
     CUDA_TRY(cudaMemcpyAsync(hist_host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int cmbpo_rollout_diagnostics(cmbpo_ctx* ctx, const cmbpo_rollout_bufs* bufs, int64_t B,
+                                         double* path_return, double* path_cost, double* stats_host) {
+    CMBPO_CHECK(ctx && bufs && path_return && path_cost && stats_host, "null argument");
+    double* d;
+    if (cmbpo_ws_get(ctx, 6, 8 * sizeof(double), (void**)&d)) return 1;
+    // sums start at 0; the maxima at the ordered-integer image of -inf
+    double init[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ninf; { const double x = -1e300; memcpy(&ninf, &x, 8); ninf = ninf >= 0 ? ninf : (ninf ^ 0x7fffffffffffffffLL); }
+    memcpy(&init[5], &ninf, 8); memcpy(&init[6], &ninf, 8);
+    CUDA_TRY(cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));          // `init` is a stack buffer
+    if (B > 0) {
+        rollout_diag_kernel<<<max(1, min(ctx->sm_count * 8, cdiv(B, 256))), 256, 0, ctx->stream>>>(*bufs, B, path_return, path_cost, d);
+        ctx->launches++;
+    }
+    rollout_diag_finish_kernel<<<1, 32, 0, ctx->stream>>>(d);
+    ctx->launches++;
+    CUDA_TRY(cudaMemcpyAsync(stats_host, d, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

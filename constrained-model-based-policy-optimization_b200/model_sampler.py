@@ -168,20 +168,17 @@ class ModelSampler:
             bufs.truncate(stop_step=self._n_episodes - 1)
             self._alive_now = 0
         self.pool.finish_all_device()
-        t = self.pool.engine.torch
-        T, B = bufs.T, bufs.B
-        m = (t.arange(T, device=bufs.length.device)[:, None] < bufs.length[None, :])
-        f64 = t.float64
-        self._total_rew = float((bufs.rew.to(f64) * m).sum())
-        self._total_cost = float((bufs.cost.to(f64) * m).sum())
-        self._total_Vs = float((bufs.val.to(f64) * m).sum())
-        self._total_CVs = float((bufs.cval.to(f64) * m).sum())
-        self._path_return = (bufs.rew.to(f64) * m).sum(0).cpu().numpy()
-        self._path_cost = (bufs.cost.to(f64) * m).sum(0).cpu().numpy()
-        self._total_dyn_ep_var = float((bufs.dyn_error.to(f64) * m).sum()) * bufs.O
-        self._max_dkl = float((bufs.dkl * m).max()) if self._total_samples else 0
-        csum = t.cumsum(bufs.rew.to(f64) * m, 0)
-        self._max_path_return = max(0.0, float(csum.max())) if self._total_samples else 0
+        # one pass over the valid steps on the device (float64): the host accumulators of
+        # model_sampler.py:314-333 and the sums of get_diagnostics (:89-133)
+        B = bufs.B
+        d = bufs.diagnostics()
+        self._total_rew, self._total_cost = d["rew"], d["cost"]
+        self._total_Vs, self._total_CVs = d["val"], d["cval"]
+        self._path_return = bufs.path_return.cpu().numpy()
+        self._path_cost = bufs.path_cost.cpu().numpy()
+        self._total_dyn_ep_var = d["dyn_error"] * bufs.O
+        self._max_dkl = d["max_dkl"] if self._total_samples else 0
+        self._max_path_return = max(0.0, d["max_path_return"]) if self._total_samples else 0
         self.pool.ptr = int(bufs.length.max().item()) if B else 0
 
     # ---- sample (model_sampler.py:239-375) ---------------------------------------------------

@@ -58,7 +58,10 @@ class ModelBuffer:
 
     @property
     def size(self):
-        return int(self.populated_mask.sum())
+        # number of populated cells = sum of the path lengths (no [B, T] mask is materialised)
+        if self._device_lengths:
+            return int(self.bufs.length.sum().item())
+        return int(self._length.sum())
 
     @property
     def has_room(self):
@@ -160,7 +163,8 @@ class ModelBuffer:
             out.append(e.compact(f, B, T, 1, b.length, off, n_rows))
         mu = e.compact(b.mu, B, T, A, b.length, off, n_rows)
         ls_row = self._log_std_row if self._log_std_row is not None else np.zeros(A, np.float32)
-        log_std = e.to_device(ls_row, t.float32).reshape(1, A).expand(n_rows, A).contiguous()
+        # every row of log_std is the same [A] variable (ac_network.py:119): a stride-0 view
+        log_std = e.to_device(ls_row, t.float32).reshape(1, A).expand(n_rows, A)
         out += [log_std, mu]                       # sorted pi_info keys: log_std, mu
         diag = dict(poolm_batch_size=n_rows, poolm_ret_mean=st["ret_mean"],
                     poolm_cret_mean=st["cret_mean"])
@@ -174,14 +178,21 @@ class ModelBuffer:
         buffers are recycled every second call, so a caller must consume (or copy) the arrays before
         the second next `get()` -- cmbpo.py:270 concatenates them immediately."""
         out, diag = self.get_device()
+        # log_std (index 10) is one [A] row repeated: it crosses PCIe once and is returned as a
+        # read-only broadcast view (values, shape and dtype as the reference's array)
+        ls_host = np.broadcast_to(out[10][:1].cpu().numpy().reshape(1, -1) if out[10].shape[0] else
+                                  np.zeros((1, self.act_dim), np.float32), tuple(out[10].shape))
         if not pinned:
-            res = [x.cpu().numpy() for x in out]
+            res = [ls_host if i == 10 else x.cpu().numpy() for i, x in enumerate(out)]
         else:
             t = self.engine.torch
             self._pin_gen = getattr(self, "_pin_gen", 0) ^ 1
             pool = self.__dict__.setdefault("_pin_pool", {})
             host = []
             for i, x in enumerate(out):
+                if i == 10:
+                    host.append(None)
+                    continue
                 key = (self._pin_gen, i)
                 buf = pool.get(key)
                 if buf is None or buf.numel() < x.numel() or buf.dtype != x.dtype:
@@ -191,6 +202,6 @@ class ModelBuffer:
                 h.copy_(x, non_blocking=True)
                 host.append(h)
             t.cuda.current_stream(self.engine.device).synchronize()
-            res = [h.numpy() for h in host]
+            res = [ls_host if h is None else h.numpy() for h in host]
         self.reset()
         return res, diag

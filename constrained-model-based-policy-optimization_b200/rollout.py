@@ -83,6 +83,17 @@ class RolloutBuffers:
         L.check(e.lib.cmbpo_rollout_truncate(e.h, C.byref(bufs), self.B, self.T, int(cap_step),
                                              int(cap_n), int(stop_step)))
 
+    def diagnostics(self):
+        """cmbpo_rollout_diagnostics over the valid steps: dict of float64 sums / maxima (host sync);
+        per-path returns / costs are left in self.path_return / self.path_cost (device, float64)."""
+        e = self.engine
+        st = (C.c_double * 8)()
+        bufs = self.struct()
+        L.check(e.lib.cmbpo_rollout_diagnostics(e.h, C.byref(bufs), self.B, e._p(self.path_return),
+                                                e._p(self.path_cost), st))
+        keys = ("rew", "cost", "val", "cval", "dyn_error", "max_dkl", "max_path_return", "n")
+        return dict(zip(keys, (float(x) for x in st)))
+
     def gae(self, gamma, lam, cgamma, clam, scan=L.SCAN_STRICT):
         """adv/ret/cadv/cret for every path from (length, last_val, last_cval)."""
         self.engine.gae_paths(self.rew, self.val, self.cost, self.cval, self.length, self.last_val,

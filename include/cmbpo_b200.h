@@ -202,6 +202,16 @@ int cmbpo_rollout_truncate(cmbpo_ctx* ctx, const cmbpo_rollout_bufs* bufs, int64
                            int cap_step, int64_t cap_n, int stop_step);
 
 /*
+ * Diagnostics of a finished (and truncated) rollout over the valid steps t < length[p], replacing the
+ * per-step host accumulators of ModelSampler.sample (samplers/model_sampler.py:314-333) and the
+ * sums of get_diagnostics (model_sampler.py:89-133).  path_return / path_cost: device [B] float64.
+ * stats_host[8] (host, float64): sum rew, sum cost, sum val, sum cval, sum dyn_error, max dkl,
+ * max running path return, number of steps.  Synchronises the stream.
+ */
+int cmbpo_rollout_diagnostics(cmbpo_ctx* ctx, const cmbpo_rollout_bufs* bufs, int64_t B,
+                              double* path_return, double* path_cost, double* stats_host);
+
+/*
  * GAE + cost-GAE + returns over finished paths
  * (buffers/modelbuffer.py:163-179, buffers/cpobuffer.py:179-207, utilities/utils.py:159-211).
  *   element (p, t) of every field lives at p*path_stride + t*time_stride (in floats).
