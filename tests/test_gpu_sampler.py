@@ -83,7 +83,8 @@ def test_fused_sampler_cycle(engine, key, mode, max_samples):
         for k in ("msampler/samples_added", "msampler/rollout_H_max"):
             assert gd[k] == wd[k], k
         for k in ("msampler/v_mean", "msampler/cv_mean", "msampler/ens_DKL", "msampler/rew_rate",
-                  "msampler/dyn_var_perstep", "msampler/max_dkl"):
+                  "msampler/dyn_var_perstep", "msampler/max_dkl", "msampler/max_path_return",
+                  "msampler/cost_rate"):
             assert np.isclose(gd[k], wd[k], rtol=5e-3, atol=1e-4), (k, gd[k], wd[k])
 
 

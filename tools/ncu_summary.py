@@ -1,7 +1,7 @@
 """Summarise ncu captures into the tracked profiles/ directory (the .ncu-rep files are scratch).
 
     python tools/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/r1_launches.txt
-    python tools/ncu_summary.py kernel gpurun_out/prof_k1_r1.ncu-rep profiles/r1_k1_ncu.txt [traffic.json]
+    python tools/ncu_summary.py kernel gpurun_out/prof_k1_r1.ncu-rep profiles/r1_k1_ncu.txt [traffic.json|-] [name substring]
 """
 import collections
 import csv
@@ -43,10 +43,12 @@ def launches(src, dst):
         f.write("total_us %.1f\n" % s)
 
 
-def kernel(rep, dst, traffic=None):
+def kernel(rep, dst, traffic=None, match=None):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    vals = next(r for r in rows[2:] if match is None or match in r[ki])   # first captured launch whose name matches
     d = {h: (units[i], vals[i]) for i, h in enumerate(hdr)}
     with open(dst, "w") as f:
         f.write("# ncu --set full --clock-control none, one launch; source: %s\n" % rep)
@@ -68,4 +70,5 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        kernel(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+        kernel(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None,
+               sys.argv[5] if len(sys.argv) > 5 else None)
