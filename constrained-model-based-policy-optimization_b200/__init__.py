@@ -22,6 +22,8 @@ from .model_sampler import ModelSampler
 from .rollout import RolloutBuffers
 from . import statics
 from . import dist
+from . import checkpoint
+from .checkpoint import load_pe
 
-__all__ = ["Engine", "B200PE", "B200Policy", "FakeEnv", "ModelBuffer", "CPOBuffer", "ModelSampler",
+__all__ = ["load_pe", "Engine", "B200PE", "B200Policy", "FakeEnv", "ModelBuffer", "CPOBuffer", "ModelSampler",
            "RolloutBuffers", "CmbpoError", "LIB_PATH", "statics"]

@@ -1,0 +1,108 @@
+"""Loader for the reference's PE checkpoints, so ensembles trained by the
+TF code base can drive the B200 rollout.
+
+`PE.save` (models/pens/pe.py:736-764) writes two files per model:
+  * `<name>_<timestep>.nns`  -- one `repr(FC)` per layer (models/pens/fc.py:46-50), the last one with
+    the end activation and, for a probabilistic model, HALF the real output width;
+  * `<name>_<timestep>.mat`  -- scipy `savemat` of `sess.run(nonoptvars + optvars)` under the keys
+    "0", "1", ...: nonoptvars = scaler_in (mu, var) then scaler_out (mu, var), each only if used
+    (pe.py:203-213, pens/utils.py:189-194); optvars = per layer (weights [E,in,out], biases
+    [E,1,out]) (fc.py:172-175), then (max_logvar, min_logvar) only for the NLL loss.
+Elite indices are not part of the checkpoint (they are recomputed by `PE.train`, pe.py:396-399):
+pass them in.
+"""
+import os
+import re
+
+import numpy as np
+
+from .pe import B200PE
+
+_FC = re.compile(r"FC\(output_dim=(?P<out>\d+), input_dim=(?P<inp>None|\d+), activation=(?P<act>None|'[^']*'|\"[^\"]*\"), "
+                 r"weight_decay=(?P<wd>[^,]+), ensemble_size=(?P<E>\d+)\)")
+
+
+def parse_nns(path):
+    """[(output_dim, input_dim or None, activation or None, ensemble_size)] per layer."""
+    layers = []
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if not line:
+                continue
+            m = _FC.fullmatch(line)
+            if m is None:
+                raise ValueError("unrecognised layer description in %s: %r" % (path, line))
+            act = m.group("act")
+            layers.append((int(m.group("out")), None if m.group("inp") == "None" else int(m.group("inp")),
+                           None if act == "None" else act.strip("'\""), int(m.group("E"))))
+    if not layers:
+        raise ValueError("%s describes no layers" % path)
+    return layers
+
+
+def read_pe_checkpoint(model_dir, name, timestep):
+    """Returns dict(W, b, acts, probabilistic, mu_in, var_in, mu_out, var_out, max_logvar, min_logvar)
+    as plain numpy arrays (scalers None when the model was saved without them)."""
+    from scipy.io import loadmat
+
+    stem = os.path.join(model_dir, "%s_%s" % (name, timestep))
+    layers = parse_nns(stem + ".nns")
+    mat = loadmat(stem + ".mat")
+    n = len([k for k in mat if k.isdigit()])
+    arrs = [np.asarray(mat[str(i)], np.float32) for i in range(n)]
+    L_ = len(layers)
+    n_extra = n - 2 * L_                       # scalers (0 / 2 / 4) + logvar bounds (0 / 2)
+    if n_extra not in (0, 2, 4, 6):
+        raise ValueError("%s.mat holds %d arrays for %d layers" % (stem, n, L_))
+    # the optimised variables are the LAST 2L (+2) arrays; decide by shape: layer weights are 3-D
+    tail = arrs[-2 * L_:] if all(a.ndim == 3 for a in arrs[-2 * L_::2]) else None
+    bounds = (None, None)
+    if tail is None:                           # NLL loss: (max_logvar, min_logvar) trail the layers
+        tail = arrs[-2 * L_ - 2:-2]
+        bounds = (arrs[-2], arrs[-1])
+        if not all(a.ndim == 3 for a in tail[::2]):
+            raise ValueError("%s.mat: cannot locate the layer weights" % stem)
+        n_scal = n - 2 * L_ - 2
+    else:
+        n_scal = n - 2 * L_
+    W = [np.ascontiguousarray(a) for a in tail[0::2]]
+    b = [np.ascontiguousarray(a.reshape(a.shape[0], -1)) for a in tail[1::2]]
+    acts = [l[2] for l in layers]
+    E, in_dim, last = W[0].shape[0], W[0].shape[1], W[-1].shape[2]
+    for (out, inp, _, ens), w in zip(layers[:-1], W[:-1]):
+        if w.shape[2] != out or ens != E or (inp is not None and inp != w.shape[1]):
+            raise ValueError("%s: .nns and .mat disagree on a layer shape" % stem)
+    if last == 2 * layers[-1][0]:
+        probabilistic = True
+    elif last == layers[-1][0]:
+        probabilistic = False
+    else:
+        raise ValueError("%s: last layer width %d vs described %d" % (stem, last, layers[-1][0]))
+    d_out = last // 2 if probabilistic else last
+    scal = [a.reshape(1, -1) for a in arrs[:n_scal]]
+    mu_in = var_in = mu_out = var_out = None
+    if n_scal == 4:
+        mu_in, var_in, mu_out, var_out = scal
+    elif n_scal == 2:                          # one scaler only: tell input from output by its width
+        if scal[0].shape[1] == in_dim and in_dim != d_out:
+            mu_in, var_in = scal
+        elif scal[0].shape[1] == d_out and in_dim != d_out:
+            mu_out, var_out = scal
+        else:
+            raise ValueError("%s: a single scaler of width %d is ambiguous (in %d, out %d)"
+                             % (stem, scal[0].shape[1], in_dim, d_out))
+    elif n_scal != 0:
+        raise ValueError("%s.mat: %d leading arrays are not a set of scalers" % (stem, n_scal))
+    return dict(W=W, b=b, acts=acts, probabilistic=probabilistic, mu_in=mu_in, var_in=var_in,
+                mu_out=mu_out, var_out=var_out, max_logvar=bounds[0], min_logvar=bounds[1])
+
+
+def load_pe(engine, which, model_dir, name, timestep, elite_inds=None):
+    """`PE(load_model=True)` (pe.py:87-96,121-160) for the B200 engine: reads the checkpoint and
+    uploads it into ensemble slot `which`; returns the model object FakeEnv / CPOPolicy consume."""
+    ck = read_pe_checkpoint(model_dir, name, timestep)
+    E = ck["W"][0].shape[0]
+    elites = list(range(E)) if elite_inds is None else [int(i) for i in elite_inds]
+    return B200PE(engine, which, ck["W"], ck["b"], ck["acts"], ck["probabilistic"], elites,
+                  ck["mu_in"], ck["var_in"], ck["mu_out"], ck["var_out"], name=name)

@@ -1,0 +1,27 @@
+"""GPU: an ensemble loaded from a PE.save-style checkpoint predicts exactly like the same weights
+uploaded directly (cmbpo_b200.load_pe)."""
+import numpy as np
+import pytest
+
+from oracle import cmbpo_oracle as orc
+from test_checkpoint_cpu import write_like_pe_save
+
+pytestmark = pytest.mark.gpu
+
+
+def test_loaded_checkpoint_predicts_like_direct_upload(engine, tmp_path):
+    import cmbpo_b200 as cb
+    from cmbpo_b200 import _lib as L
+    dyn, actor, v, vc = orc.make_problem(11, 17, 6, hidden=(64, 64))
+    obs, act = orc.make_states(12, 300, 17, 6, dyn)
+    x = np.concatenate([obs, act], -1)
+    direct = cb.B200PE.from_oracle_ensemble(engine, L.NET_DYN, dyn)
+    m0, v0 = direct.predict_ensemble(x)
+    write_like_pe_save(str(tmp_path), "BNN", 7, dyn, ("in", "out"), nll=True)
+    loaded = cb.load_pe(engine, L.NET_DYN, str(tmp_path), "BNN", 7, elite_inds=dyn.elite_inds)
+    m1, v1 = loaded.predict_ensemble(x)
+    assert loaded.is_probabilistic and loaded.elite_inds == [int(i) for i in dyn.elite_inds]
+    assert np.array_equal(m0, m1) and np.array_equal(v0, v1)
+    # and it matches the oracle's forward within the fp32 tolerance of the other tests
+    mo, vo = orc.pe_forward(dyn, x)
+    assert np.allclose(m1, mo, rtol=1e-3, atol=1e-4) and np.allclose(v1, vo, rtol=1e-3, atol=1e-6)
