@@ -23,7 +23,8 @@ from .rollout import RolloutBuffers
 from . import statics
 from . import dist
 from . import checkpoint
+from .archive import DeviceArchive
 from .checkpoint import load_pe
 
-__all__ = ["load_pe", "Engine", "B200PE", "B200Policy", "FakeEnv", "ModelBuffer", "CPOBuffer", "ModelSampler",
+__all__ = ["load_pe", "DeviceArchive", "Engine", "B200PE", "B200Policy", "FakeEnv", "ModelBuffer", "CPOBuffer", "ModelSampler",
            "RolloutBuffers", "CmbpoError", "LIB_PATH", "statics"]

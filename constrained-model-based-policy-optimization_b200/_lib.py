@@ -67,6 +67,11 @@ SIGNATURES = {
     "cmbpo_rollout": (_i, [_vp, C.POINTER(RolloutCfg), C.POINTER(RolloutBufs)]),
     "cmbpo_rollout_histogram": (_i, [_vp, _vp, _vp, _i64, _i, C.POINTER(_i64)]),
     "cmbpo_rollout_truncate": (_i, [_vp, C.POINTER(RolloutBufs), _i64, _i, _i, _i64, _i]),
+    "cmbpo_archive_index": (_i, [_vp, _vp, _i64, _i, _vp, _vp, C.POINTER(C.c_int64)]),
+    "cmbpo_archive_sample_epochs": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _u64, _u64, _vp]),
+    "cmbpo_archive_sample_boltz": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _u64, _u64, _vp]),
+    "cmbpo_gather_rows": (_i, [_vp, _vp, _i, _vp, _i64, _vp]),
+    "cmbpo_policy_kl_epochs": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, C.POINTER(C.c_double)]),
     "cmbpo_rollout_diagnostics": (_i, [_vp, C.POINTER(RolloutBufs), _i64, _vp, _vp, C.POINTER(C.c_double)]),
     "cmbpo_gae_paths": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _i64, _vp, _vp, _vp,
                              _d, _d, _d, _d, _vp, _vp, _vp, _vp, _i]),

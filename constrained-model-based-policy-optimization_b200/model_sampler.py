@@ -84,7 +84,10 @@ class ModelSampler:
 
     # ---- reset (model_sampler.py:203-237) ----------------------------------------------------
     def reset(self, observations):
-        observations = np.asarray(observations, np.float32)
+        # a device tensor (DeviceArchive.sample_start_states) stays on the device in fused mode
+        on_device = hasattr(observations, "is_cuda") and observations.is_cuda
+        if not (on_device and self.fused):
+            observations = np.asarray(observations.cpu() if on_device else observations, np.float32)
         self.batch_size = observations.shape[0]
         self._current_observation = observations
         self.policy.reset()

@@ -28,6 +28,11 @@ class B200Policy:
         self.log_std = np.asarray(log_std, np.float32).copy()
         self.act_dim = int(self.log_std.shape[0])
 
+    @property
+    def log_std_device(self):
+        """The actor's log_std variable [A] as a device tensor."""
+        return self.engine.to_device(self.log_std, self.engine.torch.float32)
+
     def attach_loaded(self, log_std):
         """Use networks that were already uploaded to the engine (e.g. after an NCCL broadcast)."""
         self.log_std = np.asarray(log_std, np.float32).copy()

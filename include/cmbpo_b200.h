@@ -212,6 +212,36 @@ int cmbpo_rollout_diagnostics(cmbpo_ctx* ctx, const cmbpo_rollout_bufs* bufs, in
                               double* path_return, double* path_cost, double* stats_host);
 
 /*
+ * Start-state sampling from the on-policy archive (algorithms/cmbpo.py:241-245), archive columns
+ * resident on the device.  Randomness: Philox4x32-10 keyed (seed, draw, sample index).
+ *
+ * cmbpo_archive_index: stable counting sort of the rows by epoch (CPOBuffer.epoch_archive,
+ *   buffers/cpobuffer.py:135,242; rows with epoch < 0 are empty).  sorted_idx [N] int32: row numbers
+ *   grouped by epoch, ascending inside an epoch; bin_offsets [n_bins + 1] int64 (device) and its host
+ *   copy: rows of epoch e are sorted_idx[bin_offsets[e] : bin_offsets[e + 1]].  Synchronises.
+ * cmbpo_archive_sample_epochs: CPOBuffer.epoch_batch (cpobuffer.py:466-524):
+ *   out_idx[k * B + b] = a uniform row of epoch epochs[k].
+ * cmbpo_archive_sample_boltz: distributed_batch_from_archive with a boltz_dist distribution
+ *   (cpobuffer.py:385-396, 413-463): epoch k with probability cdf[k] - cdf[k-1] (cdf [n_ep] float64,
+ *   device), then a uniform row of it == np.random.choice(N, B, p=dist) in distribution.
+ * cmbpo_gather_rows: dst[i, :] = src[idx[i], :]   (arch_dict[field][indices]).
+ * cmbpo_policy_kl_epochs: CPOPolicy.compute_DKL for a 3-D batch (cpo_policy.py:837-845,
+ *   network/ac_network.py:50-55): kl_host[k] = mean_b sum_a KL(current || archived) over the B rows of
+ *   epoch slot k; cur_mu / old_mu / old_log_std [n_ep * B, A], cur_log_std [A].  Synchronises.
+ */
+int cmbpo_archive_index(cmbpo_ctx* ctx, const int32_t* epoch, int64_t N, int n_bins,
+                        int32_t* sorted_idx, int64_t* bin_offsets, int64_t* bin_offsets_host);
+int cmbpo_archive_sample_epochs(cmbpo_ctx* ctx, const int32_t* sorted_idx, const int64_t* bin_offsets,
+                                const int32_t* epochs, int n_ep, int64_t B, uint64_t seed, uint64_t draw,
+                                int32_t* out_idx);
+int cmbpo_archive_sample_boltz(cmbpo_ctx* ctx, const int32_t* sorted_idx, const int64_t* bin_offsets,
+                               const int32_t* epochs, const double* cdf, int n_ep, int64_t B,
+                               uint64_t seed, uint64_t draw, int32_t* out_idx);
+int cmbpo_gather_rows(cmbpo_ctx* ctx, const float* src, int width, const int32_t* idx, int64_t n, float* dst);
+int cmbpo_policy_kl_epochs(cmbpo_ctx* ctx, const float* cur_mu, const float* cur_log_std, const float* old_mu,
+                           const float* old_log_std, int n_ep, int64_t B, int A, double* kl_host);
+
+/*
  * GAE + cost-GAE + returns over finished paths
  * (buffers/modelbuffer.py:163-179, buffers/cpobuffer.py:179-207, utilities/utils.py:159-211).
  *   element (p, t) of every field lives at p*path_stride + t*time_stride (in floats).

@@ -241,6 +241,32 @@ def gaussian_logp(x, mu, log_std):
     return pre.sum(axis=1).astype(F32)
 
 
+def policy_kl(actor: "Actor", obs, old_mu, old_log_std):
+    """`CPOPolicy.compute_DKL` for one 2-D batch (cpo_policy.py:837-845): the `d_kl` tensor of
+    ac_network.py:114 = gaussian_kl(mu, log_std, old_mu, old_log_std) (ac_network.py:50-55), float32."""
+    mu0 = actor_mu(actor, obs)
+    ls0 = np.asarray(actor.log_std, F32)
+    mu1, ls1 = np.asarray(old_mu, F32), np.asarray(old_log_std, F32)
+    var0, var1 = np.exp(F32(2) * ls0), np.exp(F32(2) * ls1)
+    pre = F32(0.5) * (((mu1 - mu0) ** 2 + var0) / (var1 + F32(LOGP_EPS)) - F32(1)) + ls1 - ls0
+    return F32(np.mean(np.sum(pre.astype(F32), axis=1, dtype=F32), dtype=F32))
+
+
+def epochs_list(epoch_archive):
+    """cpobuffer.py:149-154."""
+    bins = np.bincount(epoch_archive[epoch_archive >= 0])
+    return np.squeeze(np.nonzero(bins), axis=0)
+
+
+def boltz_dist(epoch_archive, kls, alpha=1):
+    """`CPOBuffer.boltz_dist` (cpobuffer.py:385-396), same numpy operations."""
+    ep_probs = np.exp(alpha * np.negative(kls))
+    ep_probs /= np.sum(ep_probs)
+    sample_p = np.bincount(epoch_archive[epoch_archive >= 0]).astype(np.float32)
+    sample_p[sample_p > 0] = ep_probs / sample_p[sample_p > 0]
+    return np.where(epoch_archive >= 0, sample_p[epoch_archive], 0)
+
+
 class OraclePolicy:
     """Inference side of `CPOPolicy` (cpo_policy.py:801-835).  `eps_fn(n)` supplies the
     standard-normal draws `tf.random_normal` would (ac_network.py:109)."""

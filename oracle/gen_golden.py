@@ -159,6 +159,30 @@ def gen_rollout(ref):
                  poolm_cret_mean=bdiag["poolm_cret_mean"], **pack_problem(dyn, actor, v, vc))
 
 
+def make_archive_case(seed, n_rows=5000, archive_size=6000, n_ep=7):
+    """Epoch labels of an archive filled by consecutive dump_to_archive calls, with unequal epoch
+    sizes, a gap in the epoch numbers and an empty tail (epoch -1)."""
+    rng = np.random.default_rng(seed)
+    sizes = rng.multinomial(n_rows, rng.dirichlet(np.ones(n_ep) * 2))
+    labels = np.concatenate([np.full(n, e + (2 if e >= 3 else 0)) for e, n in enumerate(sizes)])
+    ep = np.full(archive_size, -1, dtype=int)
+    ep[:n_rows] = labels
+    kls = np.abs(rng.normal(0.02, 0.03, n_ep))
+    kls[0] = 0.0
+    return ep, kls
+
+
+def gen_archive(ref):
+    ep, kls = make_archive_case(300)
+    buf = ref.CPOBuffer(10, len(ep), ref_stubs.Space(3), ref_stubs.Space(2))
+    buf.epoch_archive[:] = ep
+    out = {}
+    for alpha in (1, 5.0):
+        out["btz_alpha%g" % alpha] = buf.boltz_dist(kls, alpha=alpha)
+    np.savez_compressed(os.path.join(OUT, "archive_boltz.npz"), epoch_archive=ep, kls=kls,
+                        epochs_list=buf.epochs_list, min_ep=buf.min_ep, max_ep=buf.max_ep, **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_stubs.load()
@@ -167,6 +191,7 @@ def main():
     gen_cpobuffer(ref)
     gen_fakeenv(ref)
     gen_rollout(ref)
+    gen_archive(ref)
     for f in sorted(os.listdir(OUT)):
         print("%-44s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 

@@ -50,3 +50,16 @@ def test_mpi_statistics_scalar():
     ref = ref_stubs.load()
     x = np.random.default_rng(0).standard_normal(5001).astype(np.float32) * 3 + 1
     assert ref.mpi_statistics_scalar(x) == orc.stats_scalar(x)
+
+
+def test_boltz_dist_and_policy_kl_formula_live():
+    """Oracle boltz_dist / epochs_list against the reference's CPOBuffer methods on a fresh case."""
+    from oracle import gen_golden
+    ref = ref_stubs.load()
+    ep, kls = gen_golden.make_archive_case(77, n_rows=1234, archive_size=1500, n_ep=5)
+    buf = ref.CPOBuffer(10, len(ep), ref_stubs.Space(3), ref_stubs.Space(2))
+    buf.epoch_archive[:] = ep
+    assert np.array_equal(orc.epochs_list(ep), buf.epochs_list)
+    for alpha in (0.5, 1, 3):
+        a, b = orc.boltz_dist(ep, kls, alpha), buf.boltz_dist(kls, alpha=alpha)
+        assert a.dtype == b.dtype and np.array_equal(a, b)
