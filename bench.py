@@ -259,7 +259,7 @@ def run_cuda(args, rank, world, local_rank):
     n_tr = 0
     for s in range(args.steps):
         st = hot_path(s, start_dev)
-        n_tr += st["n"]
+        n_tr += st["n"]          # with N > 1 the statistics are all-reduced: already the whole-job count
     ev1.record()
     barrier()
     clk = clocks.stop()
@@ -321,6 +321,7 @@ def run_cuda(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        cnt[0] /= world          # n_tr was global on every rank (see the timed loop)
     ms, e2e_s, dyn_launch_ms, gae_launch_ms = (float(x) for x in vec)
     n_tr, e2e_n, launches = (float(x) for x in cnt)
 
