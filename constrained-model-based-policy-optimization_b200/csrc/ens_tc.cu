@@ -205,9 +205,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     uint32_t* trace_smem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + NBAR * 8 + 16);   // DBG only (1560 B)
     if (DBG && threadIdx.x < 3) trace_smem[threadIdx.x * 130] = 0;
 
-    // Warp ids: 0-15 epilogue, 16 = weight producer, 17 = MMA issuer, 18 = TMEM allocator, 19 = W2
-    // producer.  The SM's issue arbiter prefers the highest warp id, so the control warps (whose
-    // instructions gate everything else) are never starved by the 4 epilogue warps on their sub-core.
+    // Warp roles: 0 = main weight producer, 1 = layer-0/1 MMA issuer, 2 = TMEM allocator + layer-2 MMA
+    // issuer, 3 = W2 producer, 4-19 = epilogue (four warpgroups).  A warp may only touch the TMEM lane
+    // quarter (warp id % 4), which is also its sub-core, so every sub-core hosts four epilogue warps.
     const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = hw_warp;                                  // role id: 0-3 control, 4-19 epilogue
     const int nh2 = (p.parts == 1) ? 2 : 1;                    // H2 buffers (TMEM budget)

@@ -52,36 +52,60 @@ struct PolicyRowsArgs {
     float *last_val, *last_cval;
 };
 
-__global__ void policy_rows_kernel(PolicyRowsArgs a) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.N) return;
-    const float v = value_of(a.v, a.N, p), vc = value_of(a.vc, a.N, p);
-    if (a.pending) {
-        uint8_t f = a.pending[p];
-        if (f) {                                   // model_sampler.py:401-407 on s_{t+1}
-            if (f & 1) a.last_val[p] = v;
-            if (f & 2) a.last_cval[p] = vc;
-            a.pending[p] = 0;
+constexpr int POLICY_ROWS = 128;      // rows (= threads) per block of policy_rows_kernel
+
+// Phase 1, one thread per row: value heads, pending bootstraps, Gaussian head (pi, logp).  Phase 2,
+// all threads: the block's [128, O+A] slice of the dynamics input `xin` = concat(obs, pi) is one
+// contiguous range -> written with consecutive threads on consecutive floats (a per-row loop writes
+// 32 different 128-byte lines per store instruction).
+__global__ void __launch_bounds__(POLICY_ROWS) policy_rows_kernel(PolicyRowsArgs a) {
+    __shared__ float s_pi[POLICY_ROWS * CMBPO_MAX_ACT];
+    __shared__ unsigned char s_live[POLICY_ROWS];
+    const int64_t base = (int64_t)blockIdx.x * POLICY_ROWS;
+    const int64_t p = base + threadIdx.x;
+    bool live = p < a.N;
+    if (live) {
+        const float v = value_of(a.v, a.N, p), vc = value_of(a.vc, a.N, p);
+        if (a.pending) {
+            uint8_t f = a.pending[p];
+            if (f) {                                   // model_sampler.py:401-407 on s_{t+1}
+                if (f & 1) a.last_val[p] = v;
+                if (f & 2) a.last_cval[p] = vc;
+                a.pending[p] = 0;
+            }
+        }
+        live = !(a.alive && !a.alive[p]);
+        if (live) {
+            if (a.vout) a.vout[p] = v;
+            if (a.vcout) a.vcout[p] = vc;
+        }
+        live = live && a.mu_raw;
+        if (live) {
+            float mu[CMBPO_MAX_ACT], eps[CMBPO_MAX_ACT], pi[CMBPO_MAX_ACT];
+            const int64_t gid = a.path_ids ? (int64_t)a.path_ids[p] : a.path_base + p;
+            for (int i = 0; i < a.A; ++i) {
+                mu[i] = a.mu_raw[p * a.A + i];
+                eps[i] = a.eps ? a.eps[p * a.A + i] : philox_normal(a.seed, gid, a.step, RNG_STREAM_ACT, i);
+            }
+            float lp = actor_row(mu, a.log_std, eps, a.A, pi);
+            if (a.logp) a.logp[p] = lp;
+            for (int i = 0; i < a.A; ++i) {
+                if (a.pi) a.pi[p * a.A + i] = pi[i];
+                if (a.mu) a.mu[p * a.A + i] = mu[i];
+                s_pi[threadIdx.x * a.A + i] = pi[i];
+            }
         }
     }
-    if (a.alive && !a.alive[p]) return;
-    if (a.vout) a.vout[p] = v;
-    if (a.vcout) a.vcout[p] = vc;
-    if (!a.mu_raw) return;
-    float mu[CMBPO_MAX_ACT], eps[CMBPO_MAX_ACT], pi[CMBPO_MAX_ACT];
-    const int64_t gid = a.path_ids ? (int64_t)a.path_ids[p] : a.path_base + p;
-    for (int i = 0; i < a.A; ++i) {
-        mu[i] = a.mu_raw[p * a.A + i];
-        eps[i] = a.eps ? a.eps[p * a.A + i] : philox_normal(a.seed, gid, a.step, RNG_STREAM_ACT, i);
+    s_live[threadIdx.x] = live ? 1 : 0;
+    if (!a.xin) return;                             // uniform over the block
+    __syncthreads();
+    const int W = a.O + a.A;
+    const int64_t nrows = (a.N - base) < POLICY_ROWS ? (a.N - base) : POLICY_ROWS;
+    for (int idx = threadIdx.x; idx < nrows * W; idx += POLICY_ROWS) {
+        const int r = idx / W, c = idx - r * W;
+        if (!s_live[r]) continue;
+        a.xin[base * W + idx] = c < a.O ? a.obs[(base + r) * a.O + c] : s_pi[r * a.A + (c - a.O)];
     }
-    float lp = actor_row(mu, a.log_std, eps, a.A, pi);
-    if (a.logp) a.logp[p] = lp;
-    for (int i = 0; i < a.A; ++i) {
-        if (a.pi) a.pi[p * a.A + i] = pi[i];
-        if (a.mu) a.mu[p * a.A + i] = mu[i];
-        if (a.xin) a.xin[p * (a.O + a.A) + a.O + i] = pi[i];
-    }
-    if (a.xin) for (int o = 0; o < a.O; ++o) a.xin[p * (a.O + a.A) + o] = a.obs[p * a.O + o];
 }
 
 struct RawDyn {             // raw outputs [E, N, W]: row pointer of member 0 + member stride
@@ -397,7 +421,7 @@ int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precis
         a.log_std = ctx->log_std;
         a.v = make_head(v, raw + (size_t)a.N * A); a.v.ld = A;
         a.vc = make_head(vc, raw + (size_t)(1 + v.E) * a.N * A); a.vc.ld = A;
-        policy_rows_kernel<<<cdiv(a.N, 128), 128, 0, ctx->stream>>>(a);
+        policy_rows_kernel<<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -418,7 +442,7 @@ int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precis
     }
     a.mu_raw = raw_mu; a.log_std = ctx->log_std;
     a.v = make_head(v, raw_v); a.vc = make_head(vc, raw_vc);
-    policy_rows_kernel<<<cdiv(a.N, 128), 128, 0, ctx->stream>>>(a);
+    policy_rows_kernel<<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
