@@ -20,6 +20,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv and int(os.environ.get("RANK", "0")) == 0:
+    # the reference arm runs on rank 0 alone with ALL host threads; torchrun pins OMP_NUM_THREADS=1
+    # for its children, which must be undone before numpy loads its BLAS
+    for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_k] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -30,6 +36,19 @@ HIDDEN, E = (512, 512), 7
 MAXROLL = 35
 GAE = dict(gamma=0.99, lam=0.95, cost_gamma=0.97, cost_lam=0.5)
 METRIC, UNIT = "model-rollout transitions/sec", "transitions/s"
+WORKLOAD = ("BASELINE configs[1]: HalfCheetahSafe H-step model rollout + GAE/cost-GAE + advantage normalisation")
+
+
+def host_threads():
+    """Threads the numpy BLAS behind the oracle port actually uses (what `cores` reports)."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 def flop_per_transition(O=OBS, A=ACT, h=HIDDEN[0]):
@@ -143,11 +162,7 @@ def cpu_gae_ms_per_1m():
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    try:
-        import torch
-        cores = torch.get_num_threads()
-    except Exception:
-        cores = os.cpu_count()
+    cores = host_threads()
     B = args.cpu_batch
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_rollout_sample(min(B, 200))
@@ -162,10 +177,10 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "HalfCheetahSafe H-step model rollout + GAE, CPU port of the reference "
-                               "(numpy restatement of the TF graphs; TF 1.14 not installable)",
-                   "start_states_per_step": B, "maxroll": MAXROLL, "obs": OBS, "act": ACT,
-                   "ensemble": "7x(512,512) swish"},
+        "config": {"workload": WORKLOAD, "impl_note": "CPU port of the reference (numpy restatement of the TF "
+                               "graphs; TF 1.14 is not installable), bounded sample of the workload per step",
+                   "start_states_per_step": B, "maxroll": MAXROLL, "stored_steps": MAXROLL - 1, "obs": OBS,
+                   "act": ACT, "ensemble": "7x(512,512) swish, 5 elites"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d start states x %d steps per pass, %d passes" % (B, MAXROLL - 1, args.steps),
                          "gae_ms_per_1M_steps": cpu_gae_ms_per_1m()},
@@ -342,10 +357,7 @@ def run_cuda(args, rank, world, local_rank):
             scaled = int(min(20000, args.cpu_batch * 12.0 / max(cpu_dt, 1e-3)))
             cpu_n, cpu_dt = cpu_rollout_sample(scaled)
             args.cpu_batch = scaled
-        try:
-            cores = torch.get_num_threads()
-        except Exception:
-            cores = os.cpu_count()
+        cores = host_threads()
         line = {
             "metric": METRIC, "value": n_tr / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -355,8 +367,7 @@ def run_cuda(args, rank, world, local_rank):
                       "fp16x2": "f16 (tcgen05 kind::f16, f32 accumulate, packed-f16 activations)",
                       "bf16x2": "bf16 (tcgen05 kind::f16, f32 accumulate, packed-bf16 activations)"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: HalfCheetahSafe H-step model rollout + GAE/cost-GAE + "
-                                   "advantage normalisation",
+            "config": {"workload": WORKLOAD,
                        "start_states_per_gpu": B, "maxroll": T, "stored_steps": T - 1, "obs": OBS, "act": ACT,
                        "ensemble": "7x(512,512) swish, 5 elites", "policy": "tanh 128-128 + 2x(3x swish 128-128-1)",
                        "mode": "deterministic-mean, Philox noise, dkl_lim=inf", "precision": args.precision,
