@@ -39,6 +39,16 @@ METRIC, UNIT = "model-rollout transitions/sec", "transitions/s"
 WORKLOAD = ("BASELINE configs[1]: HalfCheetahSafe H-step model rollout + GAE/cost-GAE + advantage normalisation")
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def host_threads():
     """Threads the numpy BLAS behind the oracle port actually uses (what `cores` reports)."""
     try:
@@ -187,7 +197,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -395,7 +405,7 @@ def run_cuda(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clk,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
@@ -414,6 +424,12 @@ def main():
     ap.add_argument("--batch", type=int, default=100000, help="start states per GPU")
     ap.add_argument("--cpu-batch", type=int, default=500, help="start states of the bounded CPU sample")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries print at C level while the job runs
+    # (NCCL's version banner) goes to stderr; the real stdout is restored for the final print
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
