@@ -374,8 +374,7 @@ def run_cuda(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "fp16": "f16 (tcgen05 kind::f16, f32 accumulate)",
                       "bf16": "bf16 (tcgen05 kind::f16, f32 accumulate)",
-                      "fp16x2": "f16 (tcgen05 kind::f16, f32 accumulate, packed-f16 activations)",
-                      "bf16x2": "bf16 (tcgen05 kind::f16, f32 accumulate, packed-bf16 activations)"}[args.precision],
+                      }[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "start_states_per_gpu": B, "maxroll": T, "stored_steps": T - 1, "obs": OBS, "act": ACT,
@@ -420,7 +419,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16", "fp16x2", "bf16x2"])
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--batch", type=int, default=100000, help="start states per GPU")
     ap.add_argument("--cpu-batch", type=int, default=500, help="start states of the bounded CPU sample")
     args = ap.parse_args()

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("CMBPO_B200_LIB") or os.path.join(_HERE, "libcmbpo_b20
 NET_DYN, NET_V, NET_VC, NET_ACTOR = 0, 1, 2, 3
 ACT_IDS = {None: 0, "swish": 1, "tanh": 2, "ReLU": 3, "sigmoid": 4}
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "bf16x2": 3, "fp16x2": 4}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 TERM_NO_DONE, TERM_ANTSAFE = 0, 1
 COST_ZERO, COST_HCS, COST_ANTSAFE = 0, 1, 2
 END_ALIVE, END_UNCERTAIN, END_HORIZON, END_TERMINAL, END_CAPPED, END_STOPPED = range(6)

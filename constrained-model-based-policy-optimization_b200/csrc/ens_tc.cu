@@ -51,7 +51,6 @@ struct TcParams {
     const float *mu_in, *sig_in;
     float* out; long long out_member_stride;   // out[e*stride + row*Nout + c]
     int ntiles;
-    int act_x2;                // packed 16-bit activation math (precision modes *_X2)
     int member_act[CMBPO_MAX_E];   // ACT == 0 kernels (merged nets): hidden activation per member
     unsigned long long* dbg;   // optional [grid][16] cycle counters (protocol timing aid)
 };
@@ -73,9 +72,13 @@ constexpr int SMEM_TOTAL = SMEM_BAR + NBAR * 8 + 16;
         if (n_ < 64) { t_[2 + n_ * 2] = (tag); t_[3 + n_ * 2] = (uint32_t)clock64(); t_[0] = n_ + 1; } \
     }
 
+// debug builds only: 1 = also accumulate the cycles spent in every wait (perturbs the timeline),
+// 0 = event trace only (CMBPO_TC_TRACE_ONLY=1)
+__constant__ int g_tc_count_waits = 1;
+
 template <bool DBG>
 __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc) {
-    if (DBG) {
+    if (DBG && g_tc_count_waits) {
         long long t0 = clock64();
         mbar_wait(bar, parity);
         acc += (unsigned long long)(clock64() - t0);
@@ -90,39 +93,13 @@ template <int ACT> __device__ __forceinline__ float activate(float x) {
     return x;
 }
 
-// Packed 16-bit activation of two pre-activations: ONE MUFU op (tanh.approx.{f16x2,bf16x2}) and one
-// packed FMA for two elements, result already in the operand format of the next MMA.  Half the
-// MUFU / FMA-pipe load of the fp32 path at the price of one extra 16-bit rounding of the
-// pre-activation (opt-in precision modes *_X2).
-template <int FMT, int ACT>
-__device__ __forceinline__ uint32_t activate_x2(float x0, float x1) {
-    uint32_t t, th, r;
-    if (ACT == CMBPO_ACT_SWISH) { x0 *= 0.5f; x1 *= 0.5f; }
-    if (FMT == 0) {
-        x0 = fminf(fmaxf(x0, -30000.f), 30000.f);          // 2t must stay finite in fp16
-        x1 = fminf(fmaxf(x1, -30000.f), 30000.f);
-        __half2 h = __floats2half2_rn(x0, x1);
-        t = *reinterpret_cast<uint32_t*>(&h);
-        asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(t));
-        if (ACT == CMBPO_ACT_TANH) return th;
-        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(t), "r"(th));
-    } else {
-        __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-        t = *reinterpret_cast<uint32_t*>(&h);
-        asm("tanh.approx.bf16x2 %0, %1;" : "=r"(th) : "r"(t));
-        if (ACT == CMBPO_ACT_TANH) return th;
-        asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(t), "r"(th));
-    }
-    return r;
-}
-
 // 32 accumulator columns of this thread's row -> +bias, act -> 16-bit pairs -> 16 TMEM columns.
 // The accumulator buffer is released (`d_empty`) as soon as the values sit in registers; the
 // destination is only waited for (`dst_free`, may be null) right before the store.
 template <int FMT, int ACT>
 __device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32_t dst_addr,
                                         uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity,
-                                        bool x2, uint32_t* tr = nullptr) {
+                                        uint32_t* tr = nullptr) {
     uint32_t r[32];
     tmem_ld32(d_addr, r);
     tmem_ld_wait();
@@ -136,7 +113,7 @@ __device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32
     // The 32 elements are independent: straight-line code (no branch inside the loops) lets the
     // scheduler overlap the shuffle / MUFU latencies of all of them.
     float v[32];
-    if (!x2 && ACT == CMBPO_ACT_SWISH) {
+    if (ACT == CMBPO_ACT_SWISH) {
         // swish(x) = t + t tanh t with t = x/2 = fma(acc, 0.5, bias/2): 4.5 instructions per element
         // (SHFL, FFMA, MUFU, FFMA, half a packed saturating convert)
         const float hb = 0.5f * bias_lane;
@@ -144,22 +121,14 @@ __device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32
         for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), 0.5f, __shfl_sync(0xffffffffu, hb, i));
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = swish_half(v[i]);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) q[c] = Cvt<FMT>::pack(v[2 * c], v[2 * c + 1]);
-        goto store;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_lane, i);
-    if (x2) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) q[c] = activate_x2<FMT, ACT>(v[2 * c], v[2 * c + 1]);
     } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(v[i]);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_lane, i);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) q[c] = Cvt<FMT>::pack(v[2 * c], v[2 * c + 1]);
+        for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(v[i]);
     }
-store:
+#pragma unroll
+    for (int c = 0; c < 16; ++c) q[c] = Cvt<FMT>::pack(v[2 * c], v[2 * c + 1]);
     if (tr) tr[1] = (uint32_t)clock64();
     if (dst_free) { mbar_wait(dst_free, dst_parity); tc_fence_after(); }
     tmem_st16(dst_addr, q);
@@ -171,14 +140,14 @@ store:
 // ACT == 0: the activation is a per-member runtime value (merged policy ensemble)
 template <int FMT, int ACT>
 __device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, float bias_lane, uint32_t dst_addr,
-                                            uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity, bool x2,
+                                            uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity,
                                             uint32_t* tr = nullptr) {
     if (ACT != 0) {
-        drain32<FMT, ACT>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2, tr);
+        drain32<FMT, ACT>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, tr);
     } else if (act_rt == CMBPO_ACT_TANH) {
-        drain32<FMT, CMBPO_ACT_TANH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2);
+        drain32<FMT, CMBPO_ACT_TANH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity);
     } else {
-        drain32<FMT, CMBPO_ACT_SWISH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, x2);
+        drain32<FMT, CMBPO_ACT_SWISH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity);
     }
 }
 
@@ -233,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     // The CTA owns all 512 columns, so the allocation can only start at lane 0 / column 0.  Treating
     // the base as the constant 0 keeps every MMA operand address in uniform registers (a base read
     // back from shared memory forces a per-instruction R2UR waterfall, ~100 cycles per MMA).
-    if (*tmem_slot != 0u) { if (threadIdx.x == 0) printf("cmbpo: unexpected TMEM base %u\n", *tmem_slot); __trap(); }
+    if (*tmem_slot != 0u) __trap();     // (no printf: a device-side call constrains the hot loops' registers)
     constexpr uint32_t tmem = 0u;
     // Work unit = (row tile, member): the ntiles*E units are split into contiguous, equal ranges, one
     // per CTA, so the last wave is balanced to within one member (a tile-granular split leaves the
@@ -492,7 +461,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             if (new_tile && wg == 0) {
                 // XA: this row of the input, scaled (pens/utils.py:156), 16-bit, zero padded to 64
                 const float* xr = p.x + grow * p.ldx;
-#pragma unroll
+#pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
                     float v[8];
 #pragma unroll
@@ -501,7 +470,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                         float t = 0.f;
                         if (k < p.K0 && grow < p.N) {
                             t = xr[k];
-                            if (p.mu_in) t = __fdiv_rn(__fsub_rn(t, p.mu_in[k]), p.sig_in[k]);
+                            // fast division: the result is rounded to 16 bits right below (the IEEE
+                            // version is a subroutine call inside this kernel)
+                            if (p.mu_in) t = __fdividef(__fsub_rn(t, p.mu_in[k]), p.sig_in[k]);
                         }
                         v[i] = t;
                     }
@@ -532,15 +503,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
                     tc_fence_after();
                     if (half == 0) { TRACE(1 + pair, 1000 + j); }
-                    const long long td = DBG ? clock64() : 0;
+                    const long long td = (DBG && g_tc_count_waits) ? clock64() : 0;
                     drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
-                                      tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0, p.act_x2 != 0,
-                                      DBG ? dtr : nullptr);
+                                      tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0,
+                                      (DBG && g_tc_count_waits) ? dtr : nullptr);
                     if (DBG && half == 0 && pair == 0 && m == 8 && lane == 0 && (warp & 3) == 0 && p.dbg && blockIdx.x == 0) {
                         uint32_t* t_ = trace_smem + 130; uint32_t n_ = t_[0];
                         if (n_ + 3 <= 64) { for (int q_ = 0; q_ < 3; ++q_) { t_[2 + (n_ + q_) * 2] = 1200 + q_; t_[3 + (n_ + q_) * 2] = dtr[q_]; } t_[0] = n_ + 3; }
                     }
-                    if (DBG) c_drain += (unsigned long long)(clock64() - td);
+                    if (DBG && g_tc_count_waits) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar + H1_FULL);
                     if (half == 0) { TRACE(1 + pair, 1100 + j); }
@@ -559,11 +530,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
                     tc_fence_after();
                     if (half == 0) { TRACE(1 + pair, 2000 + j); }
-                    const long long td = DBG ? clock64() : 0;
+                    const long long td = (DBG && g_tc_count_waits) ? clock64() : 0;
                     drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
                                       tmem + COL_H2 + hb * 32 + half * 16 + lane_base, bar + D_EMPTY + buf,
-                                      bar + H2_EMPTY + hb, (hn & 1) ^ 1, p.act_x2 != 0);
-                    if (DBG) c_drain += (unsigned long long)(clock64() - td);
+                                      bar + H2_EMPTY + hb, (hn & 1) ^ 1);
+                    if (DBG && g_tc_count_waits) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar + H2_FULL + hb);
                     if (half == 0) { TRACE(1 + pair, 2100 + j); }
@@ -760,9 +731,9 @@ int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
 }
 
 int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* out_raw, int precision) {
-    const int act_x2 = (precision == CMBPO_PREC_FP16_X2 || precision == CMBPO_PREC_BF16_X2) ? 1 : 0;
-    if (precision == CMBPO_PREC_FP16_X2) precision = CMBPO_PREC_FP16;
-    if (precision == CMBPO_PREC_BF16_X2) precision = CMBPO_PREC_BF16;
+    CMBPO_CHECK(precision == CMBPO_PREC_FP16 || precision == CMBPO_PREC_BF16,
+                "precision %d: the packed 16-bit activation modes (*_X2) were removed -- the MUFU rate is per "
+                "element, so they gained nothing, and their code path slowed the default kernels by 4 %%", precision);
     CMBPO_CHECK(precision == CMBPO_PREC_BF16 || precision == CMBPO_PREC_FP16, "bad precision %d", precision);
     CMBPO_CHECK(net.tc_pack[precision], "tcgen05 weights not packed");
     if (N <= 0) return 0;
@@ -784,7 +755,6 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     p.out = out_raw; p.out_member_stride = (long long)N * p.Nout;
     p.ntiles = (int)((N + 127) / 128);
     p.dbg = nullptr;
-    p.act_x2 = act_x2;
     for (int i = 0; i < CMBPO_MAX_E; ++i) p.member_act[i] = net.member_act[i];
     const int act_sel = net.member_act[0] >= 0 ? 0 : net.acts[0];
     static const char* dbg_env = getenv("CMBPO_TC_DEBUG");
@@ -797,6 +767,11 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
         if (cmbpo_ws_get(ctx, 1, dbg_words * 8, (void**)&d)) return 1;
         CUDA_TRY(cudaMemsetAsync(d, 0, dbg_words * 8, ctx->stream));
         p.dbg = d;
+        {
+            static const char* to = getenv("CMBPO_TC_TRACE_ONLY");
+            const int count_waits = (to && atoi(to)) ? 0 : 1;
+            CUDA_TRY(cudaMemcpyToSymbolAsync(g_tc_count_waits, &count_waits, sizeof(int), 0, cudaMemcpyHostToDevice, ctx->stream));
+        }
         if (dbg_big ? launch_tc<512, 0, CMBPO_ACT_SWISH, true>(ctx, p) : launch_tc<512, 0, 0, true, 4>(ctx, p)) return 1;
         std::vector<unsigned long long> h(dbg_words);
         CUDA_TRY(cudaMemcpyAsync(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));

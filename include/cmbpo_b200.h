@@ -46,8 +46,8 @@ enum { CMBPO_ACT_NONE = 0, CMBPO_ACT_SWISH = 1, CMBPO_ACT_TANH = 2, CMBPO_ACT_RE
 enum { CMBPO_PREC_FP32 = 0,   /* CUDA-core fp32: the variant that isolates logic from precision */
        CMBPO_PREC_BF16 = 1,   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
        CMBPO_PREC_FP16 = 2,   /* tcgen05 kind::f16, fp16 operands (tf32-class mantissa), fp32 accumulate */
-       CMBPO_PREC_BF16_X2 = 3, /* as BF16 / FP16, with the hidden activations evaluated in packed 16-bit */
-       CMBPO_PREC_FP16_X2 = 4 }; /* arithmetic (one MUFU per two elements): throughput modes */
+       CMBPO_PREC_BF16_X2 = 3, /* reserved (removed: packed 16-bit activation arithmetic gained nothing -- */
+       CMBPO_PREC_FP16_X2 = 4 }; /* the MUFU rate is per element); passing them is an error */
 
 /* models/statics.py:56-70 */
 enum { CMBPO_TERM_NO_DONE = 0, CMBPO_TERM_ANTSAFE = 1 };

@@ -16,7 +16,7 @@ def _err(got, want, sig):
 
 
 @pytest.mark.parametrize("key", ["hcs", "ant", "hum"])
-@pytest.mark.parametrize("prec,vtol", [("fp16", 1e-3), ("bf16", 1e-2), ("fp16x2", 2e-3)])
+@pytest.mark.parametrize("prec,vtol", [("fp16", 1e-3), ("bf16", 1e-2)])
 def test_predict_ensemble_tc(engine, key, prec, vtol):
     task, O, A = TASKS[key]
     dyn, actor, v, vc = orc.make_problem(81, O, A, hidden=(512, 512), task=task)
@@ -30,7 +30,7 @@ def test_predict_ensemble_tc(engine, key, prec, vtol):
     e = _err(mean, wm, sig)
     rel_v = float(np.max(np.abs(var - wv) / wv))
     print("tc %s %s: mean err (units of tol) %.3f, var rel %.2e" % (key, prec, e, rel_v))
-    scale = {"fp16": 1.0, "fp16x2": 2.0, "bf16": 8.0}[prec]   # x2: one extra 16-bit rounding; bf16: 3 fewer mantissa bits
+    scale = {"fp16": 1.0, "bf16": 8.0}[prec]   # bf16: 3 fewer mantissa bits
     assert e <= scale, e
     assert rel_v <= vtol, rel_v
     # the value heads (128-wide nets, tanh/swish) through the same engine
