@@ -149,6 +149,7 @@ struct EnvStepArgs {
     double* dkl_sum;   // 1 double accumulator
 };
 
+template <int EC, bool FAST>
 __global__ void __launch_bounds__(ROW_THREADS, 4) env_step_kernel(EnvStepArgs a) {
     __shared__ RowShared sh;
     const int O = a.O, RB = ROW_THREADS / O;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) env_step_kernel(EnvStepArgs a)
             member = a.c.elite[pos];
             const float eps = (!a.c.deterministic && a.state_eps) ? a.state_eps[p * O + dim] : 1.0f;
             RawDyn raw(a.raw, a.N, 2 * a.c.D, p);
-            EnvDimOut d = env_dim(a.c, raw, dim, member, a.obs[p * O + dim], eps);
+            EnvDimOut d = env_dim<EC, FAST>(a.c, raw, dim, member, a.obs[p * O + dim], eps);
             sh.kl[threadIdx.x] = d.kl; sh.epv[threadIdx.x] = d.epv; sh.nx[threadIdx.x] = d.nx;
             sh.fin[threadIdx.x] = isfinite(d.nx) ? 1 : 0;
             a.next_obs[p * O + dim] = d.nx;
@@ -223,6 +224,7 @@ __host__ __device__ inline size_t step_smem_bytes(int O, int E, int W) {
     return (size_t)E * rows * W * 4 + rows * O * (3 * sizeof(float) + 1) + rows * (sizeof(int) + 1) + 16;
 }
 
+template <int EC, bool FAST>
 __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs a) {
     extern __shared__ __align__(16) unsigned char step_smem[];
     const int O = a.O, A = a.A, t = a.t, E = a.c.E, W = 2 * a.c.D;
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs 
                 eps = a.state_eps ? a.state_eps[p * O + dim]
                                   : philox_normal(a.seed, a.path_base + p, t, RNG_STREAM_STATE, dim);
             RawStaged raw(s_raw, rows, W, r);
-            const EnvDimOut d = env_dim(a.c, raw, dim, member, a.cur_obs[p * O + dim], eps);
+            const EnvDimOut d = env_dim<EC, FAST>(a.c, raw, dim, member, a.cur_obs[p * O + dim], eps);
             s_kl[idx] = d.kl; s_epv[idx] = d.epv; s_nx[idx] = d.nx;
             s_fin[idx] = isfinite(d.nx) ? 1 : 0;
         }
@@ -494,7 +496,11 @@ extern "C" int cmbpo_fakeenv_step(cmbpo_ctx* ctx, const cmbpo_env_cfg* cfg, cons
     a.seed = seed; a.step = step;
     a.next_obs = next_obs; a.rew = rew; a.cost = cost; a.term = term; a.dkl_path = dkl_path;
     a.ep_var = ep_var; a.dkl_sum = dsum;
-    env_step_kernel<<<min(cdiv(N, ROW_THREADS / O), ctx->sm_count * 16), ROW_THREADS, 0, ctx->stream>>>(a);
+    {
+        const int grid = min(cdiv(N, ROW_THREADS / O), ctx->sm_count * 16);
+        if (a.c.kl_closed_form && a.c.E == 7) env_step_kernel<7, true><<<grid, ROW_THREADS, 0, ctx->stream>>>(a);
+        else { a.c.kl_closed_form = 0; env_step_kernel<0, false><<<grid, ROW_THREADS, 0, ctx->stream>>>(a); }
+    }
     if (dkl_mean_out) finish_mean_kernel<<<1, 32, 0, ctx->stream>>>(dsum, N, dkl_mean_out);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -555,14 +561,17 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
         sa.b = *bufs;
         {
             const size_t smem = step_smem_bytes(O, dyn.E, 2 * dyn.D);
-            static size_t smem_max = 0;
-            if (smem > smem_max) {
+            const bool fast = sa.c.kl_closed_form && sa.c.E == 7;
+            if (!fast) sa.c.kl_closed_form = 0;      // other ensemble sizes: the exact (all-pairs) variant
+            auto kern = fast ? rollout_step_kernel<7, true> : rollout_step_kernel<0, false>;
+            static size_t smem_max[2] = {0, 0};
+            if (smem > smem_max[fast]) {
                 CMBPO_CHECK(smem <= 200 * 1024, "rollout step: obs dim / ensemble too large for the staging buffer");
-                CUDA_TRY(cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                smem_max = smem;
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                smem_max[fast] = smem;
             }
             ProfScope prof(ctx, CMBPO_PROF_STEP);
-            rollout_step_kernel<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), STEP_THREADS, smem, ctx->stream>>>(sa);
+            kern<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), STEP_THREADS, smem, ctx->stream>>>(sa);
         }
         ctx->launches++;
     }

@@ -159,8 +159,10 @@ __device__ inline float np_sum_ptr(const float* a, int n) {
 // ------------------------------------------------------------------------------------------
 struct EnvDimOut { float kl, epv, nx; };
 
-// EC > 0: ensemble size known at compile time (loops fully unrolled, no predicates); EC == 0: runtime E
-template <int EC, class Raw>
+// EC > 0: ensemble size known at compile time (loops fully unrolled, no predicates); EC == 0: runtime E.
+// FAST (the tensor-core precision modes): closed-form KL and approximate divisions (2 ulp) -- the IEEE
+// division is a subroutine call per use, and the all-pairs loop is 49 x 12 instructions of code.
+template <int EC, bool FAST, class Raw>
 __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int o, int member, float obs_o, float eps) {
     constexpr int EMAX = EC > 0 ? EC : CMBPO_MAX_E;
     const int E = EC > 0 ? EC : c.E;
@@ -195,7 +197,7 @@ __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int 
     float s = 0.f;
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) if (e < E) s = (e == 0) ? nd[0] : __fadd_rn(s, nd[e]);
-    const float m = __fdiv_rn(s, (float)E);
+    const float m = FAST ? __fdividef(s, (float)E) : __fdiv_rn(s, (float)E);
     float q = 0.f;
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) if (e < E) {
@@ -204,8 +206,8 @@ __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int 
         q = (e == 0) ? d2 : __fadd_rn(q, d2);
     }
     EnvDimOut out;
-    out.epv = __fdiv_rn(q, (float)E);
-    if (c.kl_closed_form) {
+    out.epv = FAST ? __fdividef(q, (float)E) : __fdiv_rn(q, (float)E);
+    if (FAST) {
         // sum_{i,j} KL(N_i||N_j) without the O(E^2) loop: the log-std terms cancel and
         // sum_i (mu_j-mu_i)^2 = E d_j^2 + Q with d = mu - mean(mu), Q = sum d_i^2, so
         //   sum = 0.5 * sum_j (E d_j^2 + Q + sum_i var_i) / (var_j + 1e-10) - 0.5 E^2 .
@@ -223,7 +225,7 @@ __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int 
         }
         float tot = fmaf(0.5f, acc2, -0.5f * (float)(E * E));
         tot = (tot != tot) ? tot : fminf(fmaxf(tot, 0.0f), 1e10f * (float)(E * E));
-        out.kl = __fdiv_rn(tot, (float)((double)(E * (E - 1)) + 1e-10));
+        out.kl = __fdividef(tot, (float)((double)(E * (E - 1)) + 1e-10));
         out.nx = c.predicts_delta ? __fadd_rn(sel, obs_o) : sel;
         return out;
     }
@@ -249,14 +251,11 @@ __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int 
     return out;
 }
 
-template <class Raw>
-__device__ inline EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o, int member, float obs_o, float eps) {
-    switch (c.E) {                      // the ensemble sizes the configs use (7 dynamics members; 5; 3)
-        case 7: return env_dim_t<7>(c, raw, o, member, obs_o, eps);
-        case 5: return env_dim_t<5>(c, raw, o, member, obs_o, eps);
-        case 3: return env_dim_t<3>(c, raw, o, member, obs_o, eps);
-        default: return env_dim_t<0>(c, raw, o, member, obs_o, eps);
-    }
+// Kernels are instantiated for (EC = 7, FAST) -- the 7-member ensemble of every config in the
+// tensor-core precision modes -- and for (EC = 0, exact): runtime E, IEEE divisions, all-pairs KL.
+template <int EC, bool FAST, class Raw>
+__device__ __forceinline__ EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o, int member, float obs_o, float eps) {
+    return env_dim_t<EC, FAST>(c, raw, o, member, obs_o, eps);
 }
 
 // row-owner part: ordered reductions over the O dimensions (numpy order), statics, reward
