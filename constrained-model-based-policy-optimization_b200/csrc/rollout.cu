@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) env_step_kernel(EnvStepArgs a)
         __syncthreads();
         if (active && dim == 0) {
             RawDyn raw(a.raw, a.N, 2 * a.c.D, p);
-            EnvRowOut r = env_row_finish(a.c, raw, member, sh.kl + rb * O, sh.epv + rb * O, sh.nx + rb * O,
+            EnvRowOut r = env_row_finish<FAST>(a.c, raw, member, sh.kl + rb * O, sh.epv + rb * O, sh.nx + rb * O,
                                          sh.fin + rb * O);
             a.rew[p] = r.rew; a.cost[p] = r.cost; a.term[p] = r.term ? 1 : 0;
             a.dkl_path[p] = r.dkl_path;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs 
             const int r = threadIdx.x;
             const int64_t p = base + r;
             RawStaged raw(s_raw, rows, W, r);
-            const EnvRowOut o = env_row_finish(a.c, raw, s_member[r], s_kl + r * O, s_epv + r * O, s_nx + r * O,
+            const EnvRowOut o = env_row_finish<FAST>(a.c, raw, s_member[r], s_kl + r * O, s_epv + r * O, s_nx + r * O,
                                                s_fin + r * O);
             const float v = pf_v, vc = pf_vc;
             // uncertainty cut-off BEFORE the step is stored (model_sampler.py:275-290)

@@ -181,7 +181,11 @@ __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int 
             pm += es; pv += es;
             const float var = __expf(logvar);                                    // pe.py:833
             float x = mean;
-            if (!c.deterministic) x = __fadd_rn(mean, __fmul_rn(sqrtf(var), eps));   // fake_env.py:104-106
+            if (!c.deterministic) {                                              // fake_env.py:104-106
+                // FAST: var * rsqrt(var) (2 ulp) -- the IEEE square root is a subroutine call
+                const float sd = FAST ? ((var > 0.f && !isinf(var)) ? __fmul_rn(var, rsqrtf(var)) : var) : sqrtf(var);
+                x = __fadd_rn(mean, __fmul_rn(sd, eps));
+            }
             nd[e] = x;
             // log_std = clip(log(sqrt(var)), -100, 1e8) (pens/utils.py:46-47); var = exp(2 log_std)
             float l = 0.5f * logvar, v2 = var;
@@ -259,15 +263,16 @@ __device__ __forceinline__ EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o,
 }
 
 // row-owner part: ordered reductions over the O dimensions (numpy order), statics, reward
-template <class Raw>
+template <bool FAST, class Raw>
 __device__ inline EnvRowOut env_row_finish(const EnvRowCfg& c, Raw raw, int member, const float* kl,
                                            const float* epv, const float* nx, const unsigned char* fin) {
     const int O = c.O;
     EnvRowOut r;
-    r.dkl_path = __fdiv_rn(np_sum_ptr(kl, O), (float)O);                         // fake_env.py:113
+    const float ks = np_sum_ptr(kl, O);
+    r.dkl_path = FAST ? __fdividef(ks, (float)O) : __fdiv_rn(ks, (float)O);      // fake_env.py:113
     const float es = np_sum_ptr(epv, O);
     r.ep_var_sum = es;
-    r.ep_var_mean = __fdiv_rn(es, (float)O);                                     // model_sampler.py:343
+    r.ep_var_mean = FAST ? __fdividef(es, (float)O) : __fdiv_rn(es, (float)O);   // model_sampler.py:343
     bool all_finite = true;
     for (int o = 0; o < O; ++o) all_finite = all_finite && fin[o];
     auto notdone = [&]() {                                                       // statics.py:24-27
