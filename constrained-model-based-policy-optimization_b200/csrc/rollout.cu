@@ -83,9 +83,10 @@ __global__ void __launch_bounds__(POLICY_ROWS) policy_rows_kernel(PolicyRowsArgs
         if (live) {
             float mu[CMBPO_MAX_ACT], eps[CMBPO_MAX_ACT], pi[CMBPO_MAX_ACT];
             const int64_t gid = a.path_ids ? (int64_t)a.path_ids[p] : a.path_base + p;
+            if (!a.eps) philox_normals(a.seed, gid, a.step, RNG_STREAM_ACT, a.A, eps);
             for (int i = 0; i < a.A; ++i) {
                 mu[i] = a.mu_raw[p * a.A + i];
-                eps[i] = a.eps ? a.eps[p * a.A + i] : philox_normal(a.seed, gid, a.step, RNG_STREAM_ACT, i);
+                if (a.eps) eps[i] = a.eps[p * a.A + i];
             }
             float lp = actor_row(mu, a.log_std, eps, a.A, pi);
             if (a.logp) a.logp[p] = lp;

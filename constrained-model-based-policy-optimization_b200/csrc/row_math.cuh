@@ -52,6 +52,26 @@ __device__ inline float philox_normal(uint64_t seed, int64_t path, int step, int
     return (k & 1) ? z1 : z0;
 }
 
+// the first n standard normals of (path, step, stream): one Philox block and two Box-Muller pairs per
+// four values -- same values as philox_normal(k), without recomputing the block for every k
+__device__ inline void philox_normals(uint64_t seed, int64_t path, int step, int stream, int n, float* z) {
+    for (int k0 = 0; k0 < n; k0 += 4) {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)path, (uint32_t)((uint64_t)path >> 32), (uint32_t)step,
+                      ((uint32_t)stream << 16) | (uint32_t)(k0 >> 2), (uint32_t)seed,
+                      (uint32_t)(seed >> 32), o);
+        float a0, a1, b0, b1;
+        box_muller(o[0], o[1], a0, a1);
+        z[k0] = a0;
+        if (k0 + 1 < n) z[k0 + 1] = a1;
+        if (k0 + 2 < n) {
+            box_muller(o[2], o[3], b0, b1);
+            z[k0 + 2] = b0;
+            if (k0 + 3 < n) z[k0 + 3] = b1;
+        }
+    }
+}
+
 // uniform elite position in [0, n_elite): what np.random.choice(elite_inds, N) draws (fake_env.py:176)
 __device__ inline int philox_elite_pos(uint64_t seed, int64_t path, int step, int n_elite) {
     uint32_t o[4];
