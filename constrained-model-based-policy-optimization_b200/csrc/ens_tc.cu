@@ -212,6 +212,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     const long long n_units = (long long)p.ntiles * n_groups;
     const long long u0 = n_units * blockIdx.x / gridDim.x, u1 = n_units * (blockIdx.x + 1) / gridDim.x;
 
+    // (The pool is the CTA's own allocation of 640 x 96 registers: the 4 x 128 x (96 - 64) released by the
+    // control warpgroup are exactly the 4 x 128 x 8 the epilogue warpgroups request; asking for more
+    // blocks setmaxnreg.inc forever.)
     // Register re-balancing (per warpgroup): the control warpgroup needs few registers, the epilogue
     // warps need enough to keep all 32 element chains of a drain in flight (at the 96 of the launch
     // bound ptxas serialises them through one temporary: ~2000 instead of ~500 cycles per drain).
