@@ -51,7 +51,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     // rolled: ptxas unrolls this loop 64x otherwise (2 KB of code per wait site, ~40 KB per kernel)
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    // a try_wait suspends for up to ~9 us (measured: 2^26 spins = 9.6 min): 2^19 spins trap a deadlock
+    // after ~4.5 s, three orders of magnitude above any legitimate wait
+    for (uint32_t spin = 0; spin < (1u << 19); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
