@@ -274,14 +274,23 @@ __global__ void stats_pass2_kernel(const float* __restrict__ adv, int64_t n_path
     if (threadIdx.x == 0) partial[blockIdx.x] = ss;
 }
 
-// fixed-order final reduction -> deterministic for a fixed grid
-__global__ void stats_final_kernel(const double* __restrict__ partial, int n_blocks, int width,
-                                   int stride, double* __restrict__ out, int out_offset) {
-    int c = threadIdx.x;
-    if (c >= width) return;
-    double s = 0;
-    for (int b = 0; b < n_blocks; ++b) s += partial[(size_t)b * stride + c];
-    out[out_offset + c] = s;
+// fixed-order final reduction -> deterministic for a fixed grid: thread t sums blocks t, t+256, ...
+// in order, then a fixed shared-memory tree (one block; `width` columns handled one after the other)
+__global__ void __launch_bounds__(256) stats_final_kernel(const double* __restrict__ partial, int n_blocks, int width,
+                                                          int stride, double* __restrict__ out, int out_offset) {
+    __shared__ double sh[256];
+    for (int c = 0; c < width; ++c) {
+        double s = 0;
+        for (int b = threadIdx.x; b < n_blocks; b += 256) s += partial[(size_t)b * stride + c];
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[out_offset + c] = sh[0];
+        __syncthreads();
+    }
 }
 
 __global__ void normalise_kernel(float* __restrict__ adv, float* __restrict__ cadv, int64_t n_paths,
@@ -466,7 +475,7 @@ extern "C" int cmbpo_adv_stats_pass1(cmbpo_ctx* ctx, const float* adv, const flo
     if (cmbpo_ws_get(ctx, 7, (size_t)blocks * 8 * sizeof(double), (void**)&partial)) return 1;
     stats_pass1_kernel<<<blocks, threads, 0, ctx->stream>>>(adv, cadv, ret, cret, n_paths, max_len,
                                                           path_stride, time_stride, length, partial);
-    stats_final_kernel<<<1, 32, 0, ctx->stream>>>(partial, blocks, 8, 8, sums_out, 0);
+    stats_final_kernel<<<1, 256, 0, ctx->stream>>>(partial, blocks, 8, 8, sums_out, 0);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -482,7 +491,7 @@ extern "C" int cmbpo_adv_stats_pass2(cmbpo_ctx* ctx, const float* adv, int64_t n
     if (cmbpo_ws_get(ctx, 7, (size_t)blocks * 8 * sizeof(double), (void**)&partial)) return 1;
     stats_pass2_kernel<<<blocks, threads, 0, ctx->stream>>>(adv, n_paths, max_len, path_stride,
                                                           time_stride, length, adv_mean, partial);
-    stats_final_kernel<<<1, 32, 0, ctx->stream>>>(partial, blocks, 1, 1, sums_out, 5);
+    stats_final_kernel<<<1, 256, 0, ctx->stream>>>(partial, blocks, 1, 1, sums_out, 5);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return 0;
