@@ -205,3 +205,54 @@ class ModelBuffer:
             res = [ls_host if h is None else h.numpy() for h in host]
         self.reset()
         return res, diag
+
+    def get_async(self):
+        """`get()` split in two so that the device->host copy of this batch overlaps the NEXT
+        rollout batch (algorithms/cmbpo.py:251-270 rolls several batches per epoch and only
+        concatenates their sample lists): statistics / normalisation / compaction run now on the
+        engine's stream, the copies into page-locked buffers are queued on a side stream, the buffer
+        resets.  Returns a handle whose `result()` waits for the copies and returns exactly what
+        `get()` returns.  At most two handles may be outstanding (two pinned buffer sets)."""
+        out, diag = self.get_device()
+        t, dev = self.engine.torch, self.engine.device
+        ls_row = out[10][:1].cpu().numpy().reshape(1, -1) if out[10].shape[0] else np.zeros((1, self.act_dim), np.float32)
+        ls_host = np.broadcast_to(ls_row, tuple(out[10].shape))
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = t.cuda.Stream(device=dev)
+        self._pin_gen = getattr(self, "_pin_gen", 0) ^ 1
+        pool = self.__dict__.setdefault("_pin_pool", {})
+        main = t.cuda.current_stream(dev)
+        ready = t.cuda.Event()
+        ready.record(main)                          # compaction kernels of this batch are queued
+        host = []
+        with t.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            for i, x in enumerate(out):
+                if i == 10:
+                    host.append(None)
+                    continue
+                key = (self._pin_gen, i)
+                buf = pool.get(key)
+                if buf is None or buf.numel() < x.numel() or buf.dtype != x.dtype:
+                    buf = t.empty(max(x.numel(), 1), dtype=x.dtype, pin_memory=True)
+                    pool[key] = buf
+                h = buf[:x.numel()].view(x.shape)
+                h.copy_(x, non_blocking=True)
+                x.record_stream(self._copy_stream)  # the allocator must not recycle x before the copy ran
+                host.append(h)
+            done = t.cuda.Event()
+            done.record(self._copy_stream)
+        self.reset()
+        return PendingGet(done, host, ls_host, diag, out)
+
+
+class PendingGet:
+    """Handle of `ModelBuffer.get_async()`."""
+
+    def __init__(self, done, host, ls_host, diag, keep_alive):
+        self._done, self._host, self._ls, self._diag, self._keep = done, host, ls_host, diag, keep_alive
+
+    def result(self):
+        self._done.synchronize()
+        self._keep = None
+        return [self._ls if h is None else h.numpy() for h in self._host], self._diag

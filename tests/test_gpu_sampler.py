@@ -139,3 +139,42 @@ def test_stepwise_sampler_matches_fused(engine):
         assert a.shape == b.shape
         assert np.allclose(a, b, rtol=1e-4, atol=1e-5), i
     assert d1["msampler/samples_added"] == d2["msampler/samples_added"]
+
+
+def test_get_async_pipelines_batches_and_equals_get(engine):
+    """ModelBuffer.get_async(): the sample list of batch i is copied while batch i+1 rolls out; its
+    result() is bit-identical to get() of the same batch, with two handles outstanding."""
+    import cmbpo_b200 as cb
+    task, O, A = TASKS["hcs"]
+    B, T = 512, 12
+    dyn, actor, v, vc = orc.make_problem(91, O, A, hidden=(64, 64), task=task)
+    model, policy = load_problem(engine, dyn, actor, v, vc)
+    env = cb.FakeEnv(ShapeEnv(O, A), task, model, True, True, False)
+    pool = cb.ModelBuffer(B, O, A, T, engine=engine)
+    pool.initialize({"mu": (A,), "log_std": (A,)}, **GAE)
+    batches = [orc.make_states(92 + i, B, O, A, dyn)[0] for i in range(3)]
+
+    def run(obs, seed, asynchronous):
+        smp = cb.ModelSampler(T, B, False, logger=object(), seed=seed)
+        smp.initialize(env, policy, pool)
+        smp.reset(obs)
+        while smp.sample(None)[3]["alive_ratio"] > 0.1:
+            pass
+        smp.finish_all_paths()
+        return pool.get_async() if asynchronous else pool.get()
+
+    sync = [run(o, 5 + i, False) for i, o in enumerate(batches)]
+    sync = [([a.copy() for a in out], diag) for out, diag in sync]
+    pending, got = None, []
+    for i, o in enumerate(batches):
+        nxt = run(o, 5 + i, True)
+        if pending is not None:
+            out, diag = pending.result()
+            got.append(([a.copy() for a in out], diag))      # consume before the buffers are recycled
+        pending = nxt
+    out, diag = pending.result()
+    got.append(([a.copy() for a in out], diag))
+    for (wo, wd), (go, gd) in zip(sync, got):
+        assert wd == gd and len(wo) == len(go) == 12
+        for a, b in zip(wo, go):
+            assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b)
