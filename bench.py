@@ -232,14 +232,17 @@ def run_cuda(args, rank, world, local_rank):
         return dict(W=[bcast(w) for w in en.W], b=[bcast(b) for b in en.b], mu_in=bcast(en.mu_in),
                     var_in=bcast(en.var_in), mu_out=bcast(en.mu_out), var_out=bcast(en.var_out))
 
-    d = ens_dev(dyn)
-    eng.set_network(L.NET_DYN, d["W"], d["b"], dyn.acts, d["mu_in"], d["var_in"], d["mu_out"],
-                    d["var_out"], True, dyn.elite_inds)
-    for which, en in ((L.NET_V, v), (L.NET_VC, vc)):
-        d = ens_dev(en)
-        eng.set_network(which, d["W"], d["b"], en.acts, d["mu_in"], d["var_in"], d["mu_out"],
-                        d["var_out"], False, en.elite_inds)
-    eng.set_actor([bcast(w) for w in actor.W], [bcast(b) for b in actor.b], bcast(actor.log_std))
+    dev_nets = {L.NET_DYN: ens_dev(dyn), L.NET_V: ens_dev(v), L.NET_VC: ens_dev(vc)}
+    dev_actor = ([bcast(w) for w in actor.W], [bcast(b) for b in actor.b], bcast(actor.log_std))
+
+    def load_engine(e):
+        for which, en, prob in ((L.NET_DYN, dyn, True), (L.NET_V, v, False), (L.NET_VC, vc, False)):
+            d = dev_nets[which]
+            e.set_network(which, d["W"], d["b"], en.acts, d["mu_in"], d["var_in"], d["mu_out"],
+                          d["var_out"], prob, en.elite_inds)
+        e.set_actor(*dev_actor)
+
+    load_engine(eng)
 
     B, T = args.batch, MAXROLL
     obs_host, _ = orc.make_states(100 + rank, B, OBS, ACT, dyn)
@@ -297,10 +300,6 @@ def run_cuda(args, rank, world, local_rank):
     eng.profile(False)
 
     # ---- end to end through the public API: host start states in, host sample list out ----
-    model = cb.B200PE.view(eng, L.NET_DYN)          # view over the already-loaded dynamics slot
-    policy = cb.B200Policy(eng)
-    policy.attach_loaded(actor.log_std)
-
     class _Space:
         def __init__(self, n):
             self.shape = (n,)
@@ -308,40 +307,67 @@ def run_cuda(args, rank, world, local_rank):
     class ShapeEnv:
         observation_space, action_space = _Space(OBS), _Space(ACT)
 
-    fenv = cb.FakeEnv(ShapeEnv(), TASK, model, True, True, False)
-    pool = cb.ModelBuffer(B, OBS, ACT, T, engine=eng)
-    pool.initialize({"mu": (ACT,), "log_std": (ACT,)}, **GAE)
-    pool.reduce_fn = reduce_fn if world > 1 else None
-    smp = cb.ModelSampler(T, B, False, logger=object(), seed=7)
-    smp.path_id_base = path_base
-    smp.initialize(fenv, policy, pool)
+    # Two sampler / buffer pairs, each on its own engine (= its own CUDA stream), used alternately as a
+    # caller would to keep the GPU busy: reset() only queues the rollout, so batch i+1 rolls out while
+    # the host walks batch i through sample() / finish_all_paths() / get_async() and while the
+    # device->host copy of batch i runs on a side stream.  Every batch's H2D (start states) and D2H
+    # (sample list) are inside the timed region.
+    def make_pair(k):
+        stream = torch.cuda.current_stream(dev) if k == 0 else torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(stream):
+            e = eng if k == 0 else cb.Engine(local_rank, precision=args.precision)
+            if k:
+                load_engine(e)
+            policy = cb.B200Policy(e)
+            policy.attach_loaded(actor.log_std)
+            fenv = cb.FakeEnv(ShapeEnv(), TASK, cb.B200PE.view(e, L.NET_DYN), True, True, False)
+            pool = cb.ModelBuffer(B, OBS, ACT, T, engine=e)
+            pool.initialize({"mu": (ACT,), "log_std": (ACT,)}, **GAE)
+            pool.reduce_fn = reduce_fn if world > 1 else None
+            smp = cb.ModelSampler(T, B, False, logger=object(), seed=7 + k)
+            smp.path_id_base = path_base
+            smp.initialize(fenv, policy, pool)
+        return smp, pool, stream
 
-    def e2e_launch():
-        smp.reset(obs_host)                          # H2D of the start states, rollout launch
-        while True:
-            _, _, _, info = smp.sample(None)
-            if info["alive_ratio"] <= 0.1:
-                break
-        smp.finish_all_paths()
-        return pool.get_async()                      # D2H of the sample list queued on a side stream
+    pairs = [make_pair(0), make_pair(1)]
+    torch.cuda.synchronize()
 
-    # Pipelined over rollout batches, as cmbpo.py:251-270 consumes them: the copy of batch i runs
-    # while batch i+1 rolls out; every batch's H2D and D2H are inside the timed region.
-    e2e_launch().result()
-    e2e_launch().result()   # two warm-up passes: the two page-locked buffer sets get allocated
+    def e2e_reset(k):
+        with torch.cuda.stream(pairs[k][2]):
+            pairs[k][0].reset(obs_host)              # H2D of the start states, rollout queued
+
+    def e2e_collect(k):
+        smp, pool, stream = pairs[k]
+        with torch.cuda.stream(stream):
+            while True:
+                _, _, _, info = smp.sample(None)    # the first call waits for this pair's rollout
+                if info["alive_ratio"] <= 0.1:
+                    break
+            smp.finish_all_paths()
+            return pool.get_async()
+
+    def e2e_run(n_batches):
+        n, d2h, handles = 0, 0, []
+        e2e_reset(0)
+        for i in range(n_batches):
+            if i + 1 < n_batches:
+                e2e_reset((i + 1) & 1)
+            handles.append(e2e_collect(i & 1))
+            if len(handles) == 2:                    # at most two sample lists in flight
+                out, _ = handles.pop(0).result()
+                n += len(out[0])
+        for h in handles:
+            out, _ = h.result()
+            n += len(out[0])
+        # bytes that crossed PCIe: a stride-0 axis (log_std, one row broadcast) is not copied
+        d2h = sum(int(np.prod([m for m, st in zip(a.shape, a.strides) if st != 0] or [1])) * a.itemsize for a in out)
+        return n, d2h
+
+    e2e_run(4)              # warm-up: page-locked buffer sets of both pairs get allocated
     barrier()
     t0 = time.perf_counter()
-    e2e_n, d2h = 0, 0
     e2e_steps = max(2, min(args.steps, 10))
-    pending = None
-    for i in range(e2e_steps + 1):
-        nxt = e2e_launch() if i < e2e_steps else None
-        if pending is not None:
-            out, _ = pending.result()
-            e2e_n += len(out[0])
-            # bytes that crossed PCIe: a stride-0 axis (log_std, one row broadcast) is not copied
-            d2h = sum(int(np.prod([n for n, st in zip(a.shape, a.strides) if st != 0] or [1])) * a.itemsize for a in out)
-        pending = nxt
+    e2e_n, d2h = e2e_run(e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -402,7 +428,7 @@ def run_cuda(args, rank, world, local_rank):
                              if not skip_cpu else None),
             "e2e": {"value": e2e_n / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(obs_host.nbytes), "d2h_bytes_per_step": int(d2h),
-                    "api": "ModelSampler.reset/sample/finish_all_paths + ModelBuffer.get_async().result() (numpy in, numpy out; the D2H of batch i overlaps the rollout of batch i+1)"},
+                    "api": "ModelSampler.reset/sample/finish_all_paths + ModelBuffer.get_async().result(), numpy in / numpy out, two sampler+buffer pairs alternating (batch i+1 rolls out while batch i is collected and copied)"},
             "breakdown_ms_per_step": {"dynamics_gemm_chain": dyn_ms / args.steps, "policy_pass": pol_ms / args.steps,
                                       "row_kernel": step_ms / args.steps, "gae": gae_ms / args.steps,
                                       "note": "rank 0, CUDA events around each launch"},

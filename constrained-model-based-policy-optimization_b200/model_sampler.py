@@ -122,13 +122,19 @@ class ModelSampler:
                  seed=(self.seed << 20) + self._resets, path_id_base=self.path_id_base,
                  max_steps=steps)
         pool.adopt_device_rollout(self.policy.log_std)
-        self._hist = bufs.histogram()
+        # the rollout is only queued: reset() returns immediately, the first sample() waits for it
+        # (so a caller may prepare / finish another batch while this one runs)
+        self._hist = None
+        self._step_stats_host = None
         self._alive_now = self.batch_size
         self._stopped = False
         self._horizon_steps = steps
 
     def _counts(self, t):
         """(rows alive at the start of step t, of which cut as too uncertain at t, survivors)."""
+        if self._hist is None:                      # first use after reset(): waits for the rollout
+            self._hist = self.pool.bufs.histogram()
+            self._step_stats_host = self.pool.bufs.step_stats.cpu().numpy()
         h_len, h_unc = self._hist
         longer = int(h_len[t + 1:].sum())
         return longer + int(h_unc[t]), int(h_unc[t]), longer
@@ -153,7 +159,7 @@ class ModelSampler:
         if t + 1 >= self._horizon_steps:
             alive_after = 0
         self._alive_now = alive_after
-        stats = bufs.step_stats[t].cpu().numpy()
+        stats = self._step_stats_host[t]
         dkl_mean = stats[1] / stats[0] if stats[0] > 0 else 0.0
         info = {"ensemble_dkl_mean": np.float32(dkl_mean),
                 "alive_ratio": alive_after / self.batch_size if survivors > 0 else 0}
