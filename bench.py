@@ -208,7 +208,7 @@ def run_cuda(args, rank, world, local_rank):
     import torch.distributed as dist
     import cmbpo_b200 as cb
     from cmbpo_b200 import _lib as L
-    from oracle import cmbpo_oracle as orc     # synthetic weight generator + cpu_baseline leg only
+    from cmbpo_b200 import workload as wl      # synthetic weights / start states (no oracle on this arm)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -218,7 +218,7 @@ def run_cuda(args, rank, world, local_rank):
     t = torch
 
     # weights: generated on rank 0, broadcast once over NCCL (NVLink), then uploaded from device
-    dyn, actor, v, vc = orc.make_problem(0, OBS, ACT, hidden=HIDDEN, task=TASK)
+    dyn, actor, v, vc = wl.make_problem(0, OBS, ACT, hidden=HIDDEN, task=TASK)
 
     def bcast(a):
         x = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
@@ -245,7 +245,7 @@ def run_cuda(args, rank, world, local_rank):
     load_engine(eng)
 
     B, T = args.batch, MAXROLL
-    obs_host, _ = orc.make_states(100 + rank, B, OBS, ACT, dyn)
+    obs_host, _ = wl.make_states(100 + rank, B, OBS, ACT, dyn)
     obs_pinned = torch.from_numpy(obs_host).pin_memory()
     start_dev = obs_pinned.to(dev)
     bufs = cb.RolloutBuffers(eng, B, T, OBS, ACT)

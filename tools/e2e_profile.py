@@ -5,7 +5,7 @@ import numpy as np
 import torch
 import cmbpo_b200 as cb
 from cmbpo_b200 import _lib as L
-from oracle import cmbpo_oracle as orc
+from cmbpo_b200 import workload as orc   # synthetic problem generator (no test oracle in tools)
 
 B, T, O, A = 100000, 35, 17, 6
 dyn, actor, v, vc = orc.make_problem(0, O, A, hidden=(512, 512))

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 import cmbpo_b200 as cb
 from cmbpo_b200 import _lib as L
-from oracle import cmbpo_oracle as orc
+from cmbpo_b200 import workload as orc   # synthetic problem generator (no test oracle in tools)
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 dyn, actor, v, vc = orc.make_problem(0, 17, 6, hidden=(512, 512))

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import cmbpo_b200 as cb
 from cmbpo_b200 import _lib as L
-from oracle import cmbpo_oracle as orc
+from cmbpo_b200 import workload as orc   # synthetic problem generator (no test oracle in tools)
 
 B, T, O, A = 100000, 35, 17, 6
 dyn, actor, v, vc = orc.make_problem(0, O, A, hidden=(512, 512))
