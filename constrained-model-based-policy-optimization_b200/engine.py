@@ -284,8 +284,9 @@ class Engine:
         L.check(self.lib.cmbpo_path_offsets(self.h, self._p(length, t.int32), B, self._p(off)))
         return off
 
-    def compact(self, field, B, T, width, length, offsets, n_rows):
-        out = self.empty(n_rows, width) if width > 1 or field.dim() == 3 else self.empty(n_rows)
+    def compact(self, field, B, T, width, length, offsets, n_rows, out=None):
+        if out is None:
+            out = self.empty(n_rows, width) if width > 1 or field.dim() == 3 else self.empty(n_rows)
         L.check(self.lib.cmbpo_compact_field(self.h, self._p(field), B, T, width, self._p(length),
                                              self._p(offsets), self._p(out)))
         return out

@@ -144,8 +144,23 @@ class ModelBuffer:
         self.terminated_paths_mask[:] = True
 
     # ---- get ---------------------------------------------------------------------------------
-    def get_device(self):
-        """get() without the device->host copy: (list of 12 device tensors, diagnostics)."""
+    def _staging(self, gen, i, n_rows, width, vector):
+        """Persistent compaction target (generation `gen`, field `i`), sized for a full buffer: no
+        allocator traffic per batch (a fresh 500 MB of tensors per batch makes the caching allocator
+        call cudaMalloc / cudaFree, which synchronise the device at unpredictable moments)."""
+        pool = self.__dict__.setdefault("_compact_pool", {})
+        cap = self.batch_size * self.max_path_length
+        buf = pool.get((gen, i))
+        if buf is None or buf.numel() < cap * width:
+            buf = self.engine.empty(cap * width)
+            pool[(gen, i)] = buf
+        flat = buf[:n_rows * width]
+        return flat.view(n_rows, width) if vector else flat
+
+    def get_device(self, staging_gen=None):
+        """get() without the device->host copy: (list of 12 device tensors, diagnostics).  With
+        `staging_gen` (0 | 1) the tensors are views of persistent buffers of that generation, valid
+        until the second next call with the same generation."""
         assert self.terminated_paths_mask.all()
         e, t, b = self.engine, self.engine.torch, self.bufs
         B, T = self.batch_size, self.max_path_length
@@ -157,11 +172,14 @@ class ModelBuffer:
         off = e.path_offsets(b.length)
         n_rows = int(off[-1].item())
         O, A = self.obs_dim, self.act_dim
-        out = [e.compact(b.obs, B, T, O, b.length, off, n_rows),
-               e.compact(b.act, B, T, A, b.length, off, n_rows)]
-        for f in (b.adv, b.cadv, b.ret, b.cret, b.logp, b.val, b.cval, b.cost):
-            out.append(e.compact(f, B, T, 1, b.length, off, n_rows))
-        mu = e.compact(b.mu, B, T, A, b.length, off, n_rows)
+        def tgt(i, width, vector):
+            return None if staging_gen is None else self._staging(staging_gen, i, n_rows, width, vector)
+
+        out = [e.compact(b.obs, B, T, O, b.length, off, n_rows, tgt(0, O, True)),
+               e.compact(b.act, B, T, A, b.length, off, n_rows, tgt(1, A, True))]
+        for i, f in enumerate((b.adv, b.cadv, b.ret, b.cret, b.logp, b.val, b.cval, b.cost)):
+            out.append(e.compact(f, B, T, 1, b.length, off, n_rows, tgt(2 + i, 1, False)))
+        mu = e.compact(b.mu, B, T, A, b.length, off, n_rows, tgt(11, A, True))
         ls_row = self._log_std_row if self._log_std_row is not None else np.zeros(A, np.float32)
         # every row of log_std is the same [A] variable (ac_network.py:119): a stride-0 view
         log_std = e.to_device(ls_row, t.float32).reshape(1, A).expand(n_rows, A)
@@ -213,13 +231,13 @@ class ModelBuffer:
         engine's stream, the copies into page-locked buffers are queued on a side stream, the buffer
         resets.  Returns a handle whose `result()` waits for the copies and returns exactly what
         `get()` returns.  At most two handles may be outstanding (two pinned buffer sets)."""
-        out, diag = self.get_device()
+        self._pin_gen = getattr(self, "_pin_gen", 0) ^ 1
+        out, diag = self.get_device(staging_gen=self._pin_gen)
         t, dev = self.engine.torch, self.engine.device
         ls_row = out[10][:1].cpu().numpy().reshape(1, -1) if out[10].shape[0] else np.zeros((1, self.act_dim), np.float32)
         ls_host = np.broadcast_to(ls_row, tuple(out[10].shape))
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = t.cuda.Stream(device=dev)
-        self._pin_gen = getattr(self, "_pin_gen", 0) ^ 1
         pool = self.__dict__.setdefault("_pin_pool", {})
         main = t.cuda.current_stream(dev)
         ready = t.cuda.Event()
@@ -237,8 +255,7 @@ class ModelBuffer:
                     buf = t.empty(max(x.numel(), 1), dtype=x.dtype, pin_memory=True)
                     pool[key] = buf
                 h = buf[:x.numel()].view(x.shape)
-                h.copy_(x, non_blocking=True)
-                x.record_stream(self._copy_stream)  # the allocator must not recycle x before the copy ran
+                h.copy_(x, non_blocking=True)       # x: persistent staging buffer of this generation
                 host.append(h)
             done = t.cuda.Event()
             done.record(self._copy_stream)
