@@ -2,8 +2,9 @@
 // for one 128-row tile per CTA and all E members, with tcgen05.mma (kind::f16, fp32 accumulators in
 // TMEM).  Hidden activations never leave the SM and never touch shared memory: they live in TENSOR
 // MEMORY as the A operand of the next layer (tcgen05.mma with A from TMEM), which leaves almost all
-// of shared memory to a 24-deep ring of weight tiles streamed from L2 by the bulk-copy engine
-// (pre-swizzled tile images, plain 1-D cp.async.bulk, no tensor maps).
+// of shared memory to the rings of weight tiles streamed from L2 by the bulk-copy engine (5 x 32 KB
+// for layers 0/1, 2 x 24 KB for layer 2; pre-swizzled tile images, plain 1-D cp.async.bulk, no
+// tensor maps).
 //
 //   TMEM columns (512):   H1  [0, HD/2)      layer-0 output, 16-bit packed 2/column  (A of layer 1)
 //                         D   2 x 64         fp32 accumulator chunks (double buffered)
@@ -16,9 +17,11 @@
 //   layer 2   OUT[128 x NP] += H2(tmem) x W2[chunk rows, :]
 //             epilogue: +b2 -> raw outputs (fp32) to global
 //
-// Warp roles (384 threads): warp 0 = weight producer, warp 1 = MMA issuer (both run warp-uniform
-// loops; one lane issues), warp 2 = TMEM allocator, warps 4-11 = two epilogue warpgroups (thread <->
-// row <-> TMEM lane; each warpgroup owns 32 of a chunk's 64 columns).
+// Warp roles (640 threads): warp 0 = layer-0/1 weight producer, warp 1 = layer-0/1 MMA issuer, warp 2 =
+// TMEM allocator + layer-2 MMA issuer, warp 3 = layer-2 weight producer (setmaxnreg 64), warps 4-19 =
+// four epilogue warpgroups (setmaxnreg 104; thread <-> row <-> TMEM lane; a pair of warpgroups owns
+// one accumulator buffer, each warpgroup 32 of the chunk's 64 columns).  Work unit = (row tile,
+// member), or (row tile, group of 4 narrow members) in grouped mode.
 //
 // Replaces models/pens/fc.py:74-95 x3 + the input scaler of models/pens/utils.py:156 (fused into the
 // XA load).  The output scaler / exp are applied by the consumer (ens_head_kernel or the rollout row
