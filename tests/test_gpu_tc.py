@@ -67,3 +67,38 @@ def test_rollout_fp16_vs_fp32(engine):
         err = np.max(np.abs(na[:, t] - nb[:, t]) / np.maximum(scale, 1e-2))
         assert err <= 2e-3 * (t + 1), (t, err)
     assert (a.host("cost") != b.host("cost")).mean() < 0.02
+
+
+@pytest.mark.parametrize("num_nets,hidden,B", [(5, (256, 256), 333), (3, (128, 128), 1), (7, (512, 512), 129)])
+def test_rollout_tc_other_ensemble_shapes(engine, num_nets, hidden, B):
+    """Ensemble sizes other than 7 (generic fast row path, runtime E), widths 128 / 256 (grouped and
+    ungrouped tcgen05 kernels), row counts that are not multiples of the 128-row tile, a single row."""
+    import cmbpo_b200 as cb
+    task, O, A = TASKS["ant"]
+    T = 7
+    dyn, actor, v, vc = orc.make_problem(95, O, A, hidden=hidden, num_nets=num_nets, num_elites=max(1, num_nets - 2), task=task)
+    obs, act = orc.make_states(96, B, O, A, dyn)
+    noise = orc.TableNoise(97, T, B, A, len(dyn.elite_inds))
+    model, policy = load_problem(engine, dyn, actor, v, vc)
+    env = cb.FakeEnv(ShapeEnv(O, A), task, model, True, True, False)
+    res = {}
+    for prec in ("fp32", "fp16"):
+        bufs = cb.RolloutBuffers(engine, B, T, O, A)
+        bufs.set_inputs(obs, noise.act_eps, noise.elite_pos)
+        bufs.run(env.env_cfg(True), precision=prec)
+        engine.synchronize()
+        res[prec] = bufs
+    a, b = res["fp32"], res["fp16"]
+    la, lb = a.length.cpu().numpy(), b.length.cpu().numpy()
+    assert (la != lb).mean() <= 0.02 + 1.0 / B
+    same = la == lb
+    scale = np.maximum(np.sqrt(dyn.var_in[0, :O]), 1e-2)
+    na, nb = a.host("nextobs"), b.host("nextobs")
+    da, db = a.host("dkl"), b.host("dkl")
+    for t in range(T - 1):
+        m = same & (la > t)
+        if not m.any():
+            continue
+        err = np.max(np.abs(na[m, t] - nb[m, t]) / scale)
+        assert err <= 3e-3 * (t + 1), (t, err)
+        assert np.allclose(da[m, t], db[m, t], rtol=5e-2, atol=1e-4), t      # closed-form vs all-pairs KL, fp16 inputs
