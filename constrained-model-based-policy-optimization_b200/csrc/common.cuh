@@ -84,6 +84,9 @@ struct cmbpo_ctx {
     int A = 0;
     Workspace ws[8];            // reusable scratch slots
     int64_t launches = 0;
+    // per-context (= per-device) records of cudaFuncSetAttribute calls already made
+    size_t step_smem_max[2] = {0, 0};
+    bool gae_rows_attr_set = false;
 };
 
 // grow-only scratch

@@ -416,11 +416,10 @@ extern "C" int cmbpo_gae_paths(cmbpo_ctx* ctx, const float* rew, const float* va
     } else if (time_stride == 1 && path_stride == max_len && max_len <= 96) {
         constexpr int WARPS = 4;
         size_t smem = (size_t)WARPS * 4 * 32 * (max_len | 1) * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!ctx->gae_rows_attr_set) {
             CUDA_TRY(cudaFuncSetAttribute(gae_rows_strict_kernel<WARPS>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
+            ctx->gae_rows_attr_set = true;
         }
         int64_t blocks = (n_paths + WARPS * 32 - 1) / (WARPS * 32);
         gae_rows_strict_kernel<WARPS><<<(unsigned)blocks, WARPS * 32, smem, ctx->stream>>>(

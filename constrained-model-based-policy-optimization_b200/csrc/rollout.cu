@@ -565,11 +565,10 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
             const bool fast = sa.c.kl_closed_form && sa.c.E == 7;
             if (!fast) sa.c.kl_closed_form = 0;      // other ensemble sizes: the exact (all-pairs) variant
             auto kern = fast ? rollout_step_kernel<7, true> : rollout_step_kernel<0, false>;
-            static size_t smem_max[2] = {0, 0};
-            if (smem > smem_max[fast]) {
+            if (smem > ctx->step_smem_max[fast]) {
                 CMBPO_CHECK(smem <= 200 * 1024, "rollout step: obs dim / ensemble too large for the staging buffer");
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                smem_max[fast] = smem;
+                ctx->step_smem_max[fast] = smem;
             }
             ProfScope prof(ctx, CMBPO_PROF_STEP);
             kern<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), STEP_THREADS, smem, ctx->stream>>>(sa);
