@@ -18,8 +18,8 @@
 //             epilogue: +b2 -> raw outputs (fp32) to global
 //
 // Warp roles (640 threads): warp 0 = layer-0/1 weight producer, warp 1 = layer-0/1 MMA issuer, warp 2 =
-// TMEM allocator + layer-2 MMA issuer, warp 3 = layer-2 weight producer (setmaxnreg 64), warps 4-19 =
-// four epilogue warpgroups (setmaxnreg 104; thread <-> row <-> TMEM lane; a pair of warpgroups owns
+// TMEM allocator + layer-2 MMA issuer, warp 3 = layer-2 weight producer (setmaxnreg 32), warps 4-19 =
+// four epilogue warpgroups (setmaxnreg 112; thread <-> row <-> TMEM lane; a pair of warpgroups owns
 // one accumulator buffer, each warpgroup 32 of the chunk's 64 columns).  Work unit = (row tile,
 // member), or (row tile, group of 4 narrow members) in grouped mode.
 //
@@ -215,14 +215,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     const long long n_units = (long long)p.ntiles * n_groups;
     const long long u0 = n_units * blockIdx.x / gridDim.x, u1 = n_units * (blockIdx.x + 1) / gridDim.x;
 
-    // (The pool is the CTA's own allocation of 640 x 96 registers: the 4 x 128 x (96 - 64) released by the
-    // control warpgroup are exactly the 4 x 128 x 8 the epilogue warpgroups request; asking for more
-    // blocks setmaxnreg.inc forever.)
+    // (The pool is the CTA's own allocation of 640 x 96 registers: the 128 x (96 - 32) released by the
+    // control warpgroup are exactly the 4 x 128 x 16 the epilogue warpgroups request; asking for more
+    // blocks setmaxnreg.inc forever.  32 is enough for the control warps: their MMA / copy operands live
+    // in uniform registers.)
     // Register re-balancing (per warpgroup): the control warpgroup needs few registers, the epilogue
     // warps need enough to keep all 32 element chains of a drain in flight (at the 96 of the launch
     // bound ptxas serialises them through one temporary: ~2000 instead of ~500 cycles per drain).
     if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
         // ===== main weight producer: layer-0 and layer-1 tiles, 32 KB per stage =====
         uint32_t s = 0, ph = 0;
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         }
     }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // ===== epilogue: 4 warpgroups; pair (wg>>1) owns accumulator buffer (wg>>1), half (wg&1) its columns =====
         const int wg = (warp - 4) >> 2;
         const uint32_t pair = (uint32_t)wg >> 1, half = (uint32_t)wg & 1;
