@@ -121,10 +121,11 @@ int ens_forward_f32(cmbpo_ctx* ctx, const Net& net, const float* x, int64_t N, b
                     float* out_raw);
 // tcgen05 MLP chain (2 hidden layers), same contract
 int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* out_raw,
-                   int precision);
+                   int precision, const int64_t* n_dev = nullptr);
 bool ens_tc_supported(const Net& net);
 int ens_tc_prepare(cmbpo_ctx* ctx, Net& net);
 int policy_pack_build(cmbpo_ctx* ctx);
 void net_free(Net& n);
+// n_dev (tcgen05 precisions only): live row count in device memory, <= N; rows beyond it are skipped
 int ens_forward(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, bool x_is_3d, float* out_raw,
-                int precision);
+                int precision, const int64_t* n_dev = nullptr);

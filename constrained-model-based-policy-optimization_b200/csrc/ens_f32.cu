@@ -197,13 +197,13 @@ int ens_forward_f32(cmbpo_ctx* ctx, const Net& net, const float* x, int64_t N, b
 }
 
 int ens_forward(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, bool x_is_3d, float* out_raw,
-                int precision) {
+                int precision, const int64_t* n_dev) {
     ProfScope prof(ctx, (&net == &ctx->nets[CMBPO_NET_DYN]) ? CMBPO_PROF_DYN : -1);
-    if (precision == CMBPO_PREC_FP32) return ens_forward_f32(ctx, net, x, N, x_is_3d, out_raw);
+    if (precision == CMBPO_PREC_FP32) return ens_forward_f32(ctx, net, x, N, x_is_3d, out_raw);   // all N rows
     CMBPO_CHECK(!x_is_3d, "tcgen05 path takes 2-D inputs only");
     CMBPO_CHECK(ens_tc_supported(net),
                 "tcgen05 path needs exactly two hidden layers of equal width in {128,256,512}");
-    return ens_forward_tc(ctx, net, x, N, out_raw, precision);
+    return ens_forward_tc(ctx, net, x, N, out_raw, precision, n_dev);
 }
 
 static int raw_out(cmbpo_ctx* ctx, Net& net, int64_t N, float** raw) {

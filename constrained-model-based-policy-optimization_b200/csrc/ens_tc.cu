@@ -51,6 +51,7 @@ struct TcParams {
     const float* bias; int bias_stride;
     int E, K0, KS0, Nout, NP, parts, cps;        // parts = 2 when NP > 64; cps = chunks per W2 slot
     const float* x; long long N; int ldx;
+    const long long* n_dev;                      // optional: live row count on the device (<= N)
     const float *mu_in, *sig_in;
     float* out; long long out_member_stride;   // out[e*stride + row*Nout + c]
     int ntiles;
@@ -212,7 +213,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     // last of ceil(782/148) = 6 rounds 72% empty), and neighbouring CTAs start on different members,
     // which spreads the weight streaming over E x more L2 addresses.
     const int n_groups = (p.E + G - 1) / G;         // E itself when G == 1
-    const long long n_units = (long long)p.ntiles * n_groups;
+    // the live row count may sit in device memory (alive-row compaction of the rollout): rows beyond
+    // it are not computed; strides still use the allocated N
+    const long long n_rows = p.n_dev ? *p.n_dev : p.N;
+    const long long n_units = ((n_rows + 127) / 128) * n_groups;
     const long long u0 = n_units * blockIdx.x / gridDim.x, u1 = n_units * (blockIdx.x + 1) / gridDim.x;
 
     // (The pool is the CTA's own allocation of 640 x 96 registers: the 128 x (96 - 32) released by the
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar + OUT_EMPTY);          // accumulator free again (16 warps arrive)
-            if (mine && prev_grow < p.N) {
+            if (mine && prev_grow < n_rows) {
                 const int cb = (G > 1) ? 0 : c_begin;          // first output column of this warpgroup's slice
                 float* orow = p.out + (long long)(prev_e * G + (G > 1 ? wg : 0)) * p.out_member_stride + prev_grow * p.Nout;
                 const float* b2 = p.bias + (long long)prev_e * p.bias_stride + 2 * HD + (G > 1 ? wg * p.NP : 0);
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     for (int i = 0; i < 8; ++i) {
                         const int k = c * 8 + i;
                         float t = 0.f;
-                        if (k < p.K0 && grow < p.N) {
+                        if (k < p.K0 && grow < n_rows) {
                             t = xr[k];
                             // fast division: the result is rounded to 16 bits right below (the IEEE
                             // version is a subroutine call inside this kernel)
@@ -737,7 +741,8 @@ int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
     return 0;
 }
 
-int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* out_raw, int precision) {
+int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* out_raw, int precision,
+                   const int64_t* n_dev) {
     CMBPO_CHECK(precision == CMBPO_PREC_FP16 || precision == CMBPO_PREC_BF16,
                 "precision %d: the packed 16-bit activation modes (*_X2) were removed -- the MUFU rate is per "
                 "element, so they gained nothing, and their code path slowed the default kernels by 4 %%", precision);
@@ -758,6 +763,7 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     p.bias = net.tc_bias; p.bias_stride = group * (2 * HD + p.NP);
     p.E = net.E; p.K0 = net.dims[0]; p.KS0 = (p.K0 + 15) / 16;
     p.x = x; p.N = N; p.ldx = net.dims[0];
+    p.n_dev = reinterpret_cast<const long long*>(n_dev);
     p.mu_in = net.has_in ? net.mu_in : nullptr; p.sig_in = net.sig_in;
     p.out = out_raw; p.out_member_stride = (long long)N * p.Nout;
     p.ntiles = (int)((N + 127) / 128);

@@ -43,7 +43,9 @@ struct PolicyRowsArgs {
     int64_t path_base;
     uint64_t seed;
     int step;
-    const uint8_t* alive;      // [N] or null (all rows)
+    const uint8_t* alive;      // [paths] or null (all rows)
+    const int32_t* row_path;   // [N] compact row -> local path index, or null (row == path)
+    const int64_t* n_dev;      // live row count on the device (<= N), or null (all N rows)
     // outputs
     float *pi, *logp, *mu, *vout, *vcout;   // [N,A],[N],[N,A],[N],[N]; any may be null
     float* xin;                // [N, O+A] concat(obs, pi) or null
@@ -62,10 +64,12 @@ __global__ void __launch_bounds__(POLICY_ROWS) policy_rows_kernel(PolicyRowsArgs
     __shared__ float s_pi[POLICY_ROWS * CMBPO_MAX_ACT];
     __shared__ unsigned char s_live[POLICY_ROWS];
     const int64_t base = (int64_t)blockIdx.x * POLICY_ROWS;
-    const int64_t p = base + threadIdx.x;
-    bool live = p < a.N;
+    const int64_t r = base + threadIdx.x;          // row of the (possibly compacted) batch
+    const int64_t n_rows = a.n_dev ? *a.n_dev : a.N;
+    bool live = r < n_rows;
     if (live) {
-        const float v = value_of(a.v, a.N, p), vc = value_of(a.vc, a.N, p);
+        const int64_t p = a.row_path ? (int64_t)a.row_path[r] : r;   // path the per-path arrays are indexed by
+        const float v = value_of(a.v, a.N, r), vc = value_of(a.vc, a.N, r);
         if (a.pending) {
             uint8_t f = a.pending[p];
             if (f) {                                   // model_sampler.py:401-407 on s_{t+1}
@@ -76,23 +80,23 @@ __global__ void __launch_bounds__(POLICY_ROWS) policy_rows_kernel(PolicyRowsArgs
         }
         live = !(a.alive && !a.alive[p]);
         if (live) {
-            if (a.vout) a.vout[p] = v;
-            if (a.vcout) a.vcout[p] = vc;
+            if (a.vout) a.vout[r] = v;
+            if (a.vcout) a.vcout[r] = vc;
         }
         live = live && a.mu_raw;
         if (live) {
             float mu[CMBPO_MAX_ACT], eps[CMBPO_MAX_ACT], pi[CMBPO_MAX_ACT];
-            const int64_t gid = a.path_ids ? (int64_t)a.path_ids[p] : a.path_base + p;
+            const int64_t gid = a.path_ids ? (int64_t)a.path_ids[r] : a.path_base + p;
             if (!a.eps) philox_normals(a.seed, gid, a.step, RNG_STREAM_ACT, a.A, eps);
             for (int i = 0; i < a.A; ++i) {
-                mu[i] = a.mu_raw[p * a.A + i];
+                mu[i] = a.mu_raw[r * a.A + i];
                 if (a.eps) eps[i] = a.eps[p * a.A + i];
             }
             float lp = actor_row(mu, a.log_std, eps, a.A, pi);
-            if (a.logp) a.logp[p] = lp;
+            if (a.logp) a.logp[r] = lp;
             for (int i = 0; i < a.A; ++i) {
-                if (a.pi) a.pi[p * a.A + i] = pi[i];
-                if (a.mu) a.mu[p * a.A + i] = mu[i];
+                if (a.pi) a.pi[r * a.A + i] = pi[i];
+                if (a.mu) a.mu[r * a.A + i] = mu[i];
                 s_pi[threadIdx.x * a.A + i] = pi[i];
             }
         }
@@ -101,11 +105,12 @@ __global__ void __launch_bounds__(POLICY_ROWS) policy_rows_kernel(PolicyRowsArgs
     if (!a.xin) return;                             // uniform over the block
     __syncthreads();
     const int W = a.O + a.A;
-    const int64_t nrows = (a.N - base) < POLICY_ROWS ? (a.N - base) : POLICY_ROWS;
+    const int64_t left = n_rows - base;
+    const int64_t nrows = left < 0 ? 0 : (left < POLICY_ROWS ? left : POLICY_ROWS);
     for (int idx = threadIdx.x; idx < nrows * W; idx += POLICY_ROWS) {
-        const int r = idx / W, c = idx - r * W;
-        if (!s_live[r]) continue;
-        a.xin[base * W + idx] = c < a.O ? a.obs[(base + r) * a.O + c] : s_pi[r * a.A + (c - a.O)];
+        const int rr = idx / W, c = idx - rr * W;
+        if (!s_live[rr]) continue;
+        a.xin[base * W + idx] = c < a.O ? a.obs[(base + rr) * a.O + c] : s_pi[rr * a.A + (c - a.O)];
     }
 }
 
@@ -202,8 +207,10 @@ struct StepArgs {
     uint8_t* alive;          // [B]
     uint8_t* pending;        // [B]
     const float *pi, *mu, *logp, *v, *vc;      // this step's policy outputs [B,..]
-    const int32_t* elite_pos;                  // [B] slice for this step or null
-    const float* state_eps;                    // [B,O] slice or null
+    const int32_t* elite_pos;                  // [B] slice for this step or null (indexed by path)
+    const float* state_eps;                    // [B,O] slice or null (indexed by path)
+    const int32_t* row_path;                   // [B] compact row -> path, or null (row == path)
+    const int64_t* n_dev;                      // live row count (device), or null (B rows)
     cmbpo_rollout_bufs b;
 };
 
@@ -222,7 +229,7 @@ constexpr int STEP_THREADS = 256;     // (128-thread blocks, 8 per SM, measured 
 __host__ __device__ inline int step_rows(int O) { return 2 * STEP_THREADS / O < 64 ? 2 * STEP_THREADS / O : 64; }
 __host__ __device__ inline size_t step_smem_bytes(int O, int E, int W) {
     const size_t rows = step_rows(O);
-    return (size_t)E * rows * W * 4 + rows * O * (3 * sizeof(float) + 1) + rows * (sizeof(int) + 1) + 16;
+    return (size_t)E * rows * W * 4 + rows * O * (3 * sizeof(float) + 1) + rows * (2 * sizeof(int) + 1) + 16;
 }
 
 template <int EC, bool FAST>
@@ -236,13 +243,17 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs 
     float* s_epv = s_kl + NI;
     float* s_nx = s_epv + NI;
     int* s_member = reinterpret_cast<int*>(s_nx + NI);
-    unsigned char* s_fin = reinterpret_cast<unsigned char*>(s_member + rows);
+    int* s_path = s_member + rows;
+    unsigned char* s_fin = reinterpret_cast<unsigned char*>(s_path + rows);
     unsigned char* s_state = s_fin + NI;             // 0 = not fed, 1 = stored, 2 = cut
     __shared__ double s_stats[4];
     double st0 = 0.0, st1 = 0.0, st2 = 0.0, st3 = 0.0;   // rows fed, sum dkl, rows stored, sum ep_var
     if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
-    for (int64_t base = (int64_t)blockIdx.x * rows; base < a.B; base += (int64_t)gridDim.x * rows) {
-        const int nrows = (a.B - base) < rows ? (int)(a.B - base) : rows;
+    // rows r of the (possibly compacted) batch: raw outputs, carried state and this step's policy outputs
+    // are indexed by row; the ModelBuffer fields, alive / pending flags and injected noise by path
+    const int64_t n_live = a.n_dev ? *a.n_dev : a.B;
+    for (int64_t base = (int64_t)blockIdx.x * rows; base < n_live; base += (int64_t)gridDim.x * rows) {
+        const int nrows = (n_live - base) < rows ? (int)(n_live - base) : rows;
         const int n2 = nrows * W / 2;                // W is even: 8-byte units, always aligned
         for (int e = warp; e < E; e += STEP_THREADS / 32) {
             const float2* src = reinterpret_cast<const float2*>(a.raw + ((int64_t)e * a.B + base) * W);
@@ -259,15 +270,19 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs 
         float pf_v = 0.f, pf_vc = 0.f, pf_logp = 0.f;
         double pf_dkl = 0.0, pf_ret = 0.0, pf_cost = 0.0;
         if (threadIdx.x < rows) {
-            const int64_t p = base + threadIdx.x;
-            int member = -1;
-            if (p < a.B && a.alive[p]) {
-                const int pos = a.elite_pos ? a.elite_pos[p] : philox_elite_pos(a.seed, a.path_base + p, t, a.n_elite);
-                member = a.c.elite[pos];
-                pf_v = a.v[p]; pf_vc = a.vc[p]; pf_logp = a.logp[p];
-                pf_dkl = a.b.cum_dkl[p]; pf_ret = a.b.path_return[p]; pf_cost = a.b.path_cost[p];
+            const int64_t r = base + threadIdx.x;
+            int member = -1, path = -1;
+            if (r < n_live) {
+                path = a.row_path ? a.row_path[r] : (int)r;
+                if (a.alive[path]) {
+                    const int pos = a.elite_pos ? a.elite_pos[path] : philox_elite_pos(a.seed, a.path_base + path, t, a.n_elite);
+                    member = a.c.elite[pos];
+                    pf_v = a.v[r]; pf_vc = a.vc[r]; pf_logp = a.logp[r];
+                    pf_dkl = a.b.cum_dkl[path]; pf_ret = a.b.path_return[path]; pf_cost = a.b.path_cost[path];
+                }
             }
             s_member[threadIdx.x] = member;
+            s_path[threadIdx.x] = path;
             s_state[threadIdx.x] = 0;
         }
         __syncthreads();
@@ -275,20 +290,20 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs 
             const int r = idx / O, dim = idx - r * O;
             const int member = s_member[r];
             if (member < 0) continue;
-            const int64_t p = base + r;
+            const int64_t p = s_path[r];
             float eps = 1.0f;
             if (!a.c.deterministic)
                 eps = a.state_eps ? a.state_eps[p * O + dim]
                                   : philox_normal(a.seed, a.path_base + p, t, RNG_STREAM_STATE, dim);
             RawStaged raw(s_raw, rows, W, r);
-            const EnvDimOut d = env_dim<EC, FAST>(a.c, raw, dim, member, a.cur_obs[p * O + dim], eps);
+            const EnvDimOut d = env_dim<EC, FAST>(a.c, raw, dim, member, a.cur_obs[(base + r) * O + dim], eps);
             s_kl[idx] = d.kl; s_epv[idx] = d.epv; s_nx[idx] = d.nx;
             s_fin[idx] = isfinite(d.nx) ? 1 : 0;
         }
         __syncthreads();
         if (threadIdx.x < rows && s_member[threadIdx.x] >= 0) {
             const int r = threadIdx.x;
-            const int64_t p = base + r;
+            const int64_t p = s_path[r];
             RawStaged raw(s_raw, rows, W, r);
             const EnvRowOut o = env_row_finish<FAST>(a.c, raw, s_member[r], s_kl + r * O, s_epv + r * O, s_nx + r * O,
                                                s_fin + r * O);
@@ -325,18 +340,18 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs 
         for (int idx = threadIdx.x; idx < NI; idx += STEP_THREADS) {
             const int r = idx / O, dim = idx - r * O;
             if (s_state[r] != 1) continue;
-            const int64_t p = base + r, row = (int64_t)t * a.B + p;
+            const int64_t p = s_path[r], row = (int64_t)t * a.B + p;
             const float nx = s_nx[idx];
-            a.b.obs[row * O + dim] = a.cur_obs[p * O + dim];
+            a.b.obs[row * O + dim] = a.cur_obs[(base + r) * O + dim];
             a.b.nextobs[row * O + dim] = nx;
-            a.cur_obs[p * O + dim] = nx;                          // model_sampler.py:350
+            a.cur_obs[(base + r) * O + dim] = nx;                 // model_sampler.py:350
         }
         for (int idx = threadIdx.x; idx < rows * A; idx += STEP_THREADS) {
             const int r = idx / A, i = idx - r * A;
             if (s_state[r] != 1) continue;
-            const int64_t p = base + r, row = (int64_t)t * a.B + p;
-            a.b.act[row * A + i] = a.pi[p * A + i];
-            a.b.mu[row * A + i] = a.mu[p * A + i];
+            const int64_t p = s_path[r], row = (int64_t)t * a.B + p;
+            a.b.act[row * A + i] = a.pi[(base + r) * A + i];
+            a.b.mu[row * A + i] = a.mu[(base + r) * A + i];
         }
         __syncthreads();
     }
@@ -371,11 +386,47 @@ __global__ void rollout_init_kernel(int64_t B, int O, const float* start, float*
 // paths still alive when the step budget ran out keep END_ALIVE; their bootstrap values are
 // V(s_now), VC(s_now) so that finish_all_paths (model_sampler.py:418-444) is a no-op on the device
 __global__ void rollout_final_kernel(int64_t B, int O, const float* cur, const uint8_t* alive,
-                                     cmbpo_rollout_bufs b, const float* v, const float* vc) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= B) return;
-    if (alive[p]) { b.last_val[p] = v[p]; b.last_cval[p] = vc[p]; }
-    if (b.final_obs) for (int o = 0; o < O; ++o) b.final_obs[p * O + o] = cur[p * O + o];
+                                     cmbpo_rollout_bufs b, const float* v, const float* vc,
+                                     const int32_t* row_path, const int64_t* n_dev) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (n_dev ? *n_dev : B)) return;
+    const int64_t p = row_path ? (int64_t)row_path[r] : r;
+    if (alive[p]) { b.last_val[p] = v[r]; b.last_cval[p] = vc[r]; }
+    if (b.final_obs) for (int o = 0; o < O; ++o) b.final_obs[p * O + o] = cur[r * O + o];
+}
+
+// ---- alive-row compaction (tensor-core precisions, tasks / modes in which paths end early) ----------
+// The reference only feeds the alive paths to the networks (model_sampler.py:255-259, 300-311).  Here
+// the rows of finished paths are squeezed out of the batch every few steps: flags -> exclusive scan
+// (cmbpo_path_offsets) -> gather of the carried state and of the row -> path map; the row count
+// lives in device memory and every kernel of the step reads it, so no host round trip is needed.
+// A path that still waits for a bootstrap value (pending) stays one more policy pass.
+__global__ void compact_init_kernel(int64_t B, int32_t* row_path, int64_t* n_dev) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < B) row_path[r] = (int32_t)r;
+    if (r == 0) { n_dev[0] = B; n_dev[1] = B; }
+}
+
+__global__ void compact_flags_kernel(int64_t B, const int32_t* row_path, const int64_t* n_dev, const uint8_t* alive,
+                                     const uint8_t* pending, int32_t* flags) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    int f = 0;
+    if (r < *n_dev) { const int p = row_path[r]; f = (alive[p] || pending[p]) ? 1 : 0; }
+    flags[r] = f;
+}
+
+__global__ void compact_gather_kernel(int64_t B, int O, const int32_t* flags, const int64_t* off, const int64_t* n_old,
+                                      const float* cur, const int32_t* row_path, float* cur2, int32_t* row_path2,
+                                      int64_t* n_new) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_new = off[B];
+    const int64_t r = i / O;
+    if (r >= *n_old || !flags[r]) return;
+    const int c = (int)(i - r * O);
+    const int64_t dst = off[r];
+    cur2[dst * O + c] = cur[i];
+    if (c == 0) row_path2[dst] = row_path[r];
 }
 
 EnvRowCfg make_env_cfg(const Net& dyn, const cmbpo_env_cfg& e, int O, int precision) {
@@ -419,7 +470,7 @@ int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precis
         CMBPO_CHECK(ctx->log_std && A <= CMBPO_MAX_ACT, "actor not loaded");
         float* raw;
         if (cmbpo_ws_get(ctx, 3, (size_t)pn.E * a.N * A * sizeof(float), (void**)&raw)) return 1;
-        if (ens_forward(ctx, pn, a.obs, a.N, false, raw, precision)) return 1;
+        if (ens_forward(ctx, pn, a.obs, a.N, false, raw, precision, a.n_dev)) return 1;
         a.mu_raw = with_actor ? raw : nullptr;
         a.log_std = ctx->log_std;
         a.v = make_head(v, raw + (size_t)a.N * A); a.v.ld = A;
@@ -522,24 +573,42 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
     CMBPO_CHECK(T >= 2, "max_path_length must be >= 2");
     const int n_steps = (cfg->max_steps > 0 && cfg->max_steps < T - 1) ? cfg->max_steps : T - 1;
 
-    float *cur, *pi, *mu, *logp, *v, *vc, *xin, *raw;
+    float *cur, *cur2, *pi, *mu, *logp, *v, *vc, *xin, *raw;
     uint8_t *alive, *pending;
-    size_t fl = (size_t)B * (O + 2 * A + 3 + Din);
+    int32_t *row_path[2], *cflags;
+    int64_t *n_dev, *coff;
+    size_t fl = (size_t)B * (2 * O + 2 * A + 3 + Din);
     char* base;
-    if (cmbpo_ws_get(ctx, 5, fl * sizeof(float) + 2 * (size_t)B + 256, (void**)&base)) return 1;
-    cur = (float*)base; pi = cur + (size_t)B * O; mu = pi + (size_t)B * A; logp = mu + (size_t)B * A;
+    // floats | int64 (2 row counts + B+1 scan offsets) | int32 (2 row maps + flags) | bytes
+    const size_t bytes_f = fl * sizeof(float), bytes_l = ((size_t)B + 4) * sizeof(int64_t), bytes_i = 3 * (size_t)B * sizeof(int32_t);
+    if (cmbpo_ws_get(ctx, 5, bytes_f + bytes_l + bytes_i + 2 * (size_t)B + 256, (void**)&base)) return 1;
+    cur = (float*)base; cur2 = cur + (size_t)B * O; pi = cur2 + (size_t)B * O; mu = pi + (size_t)B * A; logp = mu + (size_t)B * A;
     v = logp + B; vc = v + B; xin = vc + B;
-    alive = (uint8_t*)(xin + (size_t)B * Din); pending = alive + B;
+    char* q = base + ((bytes_f + 15) & ~(size_t)15);
+    n_dev = (int64_t*)q; coff = n_dev + 2;
+    row_path[0] = (int32_t*)(q + bytes_l); row_path[1] = row_path[0] + B; cflags = row_path[1] + B;
+    alive = (uint8_t*)(cflags + B); pending = alive + B;
+    // alive-row compaction: only where paths can end before the horizon, and only on the tcgen05 path
+    // (the fp32 GEMM kernels take their row count from the host)
+    const bool compacting = cfg->precision != CMBPO_PREC_FP32 &&
+                            (cfg->uncertainty_mode || cfg->env.term_id != CMBPO_TERM_NO_DONE);
+    int cur_gen = 0;
     if (cmbpo_ws_get(ctx, 2, (size_t)dyn.E * B * 2 * dyn.D * sizeof(float), (void**)&raw)) return 1;
 
     CUDA_TRY(cudaMemsetAsync(bufs->step_stats, 0, (size_t)T * 4 * sizeof(double), ctx->stream));
     rollout_init_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, O, bufs->start_obs, cur, alive, pending, *bufs);
     ctx->launches++;
+    if (compacting) {
+        compact_init_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, row_path[0], n_dev);
+        ctx->launches++;
+    }
 
     for (int t = 0; t <= n_steps; ++t) {
         const bool last = (t == n_steps);
         PolicyRowsArgs pa = {};
         pa.N = B; pa.O = O; pa.A = A; pa.obs = cur;
+        pa.row_path = compacting ? row_path[cur_gen] : nullptr;
+        pa.n_dev = compacting ? n_dev + cur_gen : nullptr;
         pa.eps = (bufs->act_eps && !last) ? bufs->act_eps + (size_t)t * B * A : nullptr;
         pa.path_base = cfg->path_id_base; pa.seed = cfg->seed; pa.step = t;
         pa.alive = alive; pa.pi = pi; pa.logp = logp; pa.mu = mu; pa.vout = v; pa.vcout = vc;
@@ -549,8 +618,9 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
             if (policy_forward(ctx, pa, !last, cfg->precision)) return 1;
         }
         if (last) break;
-        if (ens_forward(ctx, dyn, xin, B, false, raw, cfg->precision)) return 1;
+        if (ens_forward(ctx, dyn, xin, B, false, raw, cfg->precision, pa.n_dev)) return 1;
         StepArgs sa = {};
+        sa.row_path = pa.row_path; sa.n_dev = pa.n_dev;
         sa.B = B; sa.O = O; sa.A = A; sa.T = T; sa.t = t; sa.last_storable = T - 2;
         sa.c = make_env_cfg(dyn, cfg->env, O, cfg->precision); sa.n_elite = dyn.n_elite;
         sa.uncertainty = cfg->uncertainty_mode; sa.dkl_lim = cfg->dkl_lim;
@@ -574,8 +644,21 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
             kern<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), STEP_THREADS, smem, ctx->stream>>>(sa);
         }
         ctx->launches++;
+        if (compacting && (t & 3) == 3 && t + 1 < n_steps) {
+            compact_flags_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, row_path[cur_gen], n_dev + cur_gen, alive, pending, cflags);
+            ctx->launches++;
+            if (cmbpo_path_offsets(ctx, cflags, B, coff)) return 1;
+            compact_gather_kernel<<<cdiv(B * O, 256), 256, 0, ctx->stream>>>(B, O, cflags, coff, n_dev + cur_gen, cur,
+                                                                            row_path[cur_gen], cur2, row_path[cur_gen ^ 1],
+                                                                            n_dev + (cur_gen ^ 1));
+            ctx->launches++;
+            std::swap(cur, cur2);
+            cur_gen ^= 1;
+        }
     }
-    rollout_final_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, O, cur, alive, *bufs, v, vc);
+    rollout_final_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, O, cur, alive, *bufs, v, vc,
+                                                                 compacting ? row_path[cur_gen] : nullptr,
+                                                                 compacting ? n_dev + cur_gen : nullptr);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
