@@ -8,6 +8,7 @@
 // Reference: samplers/model_sampler.py:239-375 (sample), 377-416 (_finish_paths),
 //            models/fake_env.py:66-172, buffers/modelbuffer.py:114-135 (store_multiple),
 //            policies/cpo_policy.py:801-835.
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "row_math.cuh"
@@ -590,7 +591,8 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
     alive = (uint8_t*)(cflags + B); pending = alive + B;
     // alive-row compaction: only where paths can end before the horizon, and only on the tcgen05 path
     // (the fp32 GEMM kernels take their row count from the host)
-    const bool compacting = cfg->precision != CMBPO_PREC_FP32 &&
+    const char* no_compact = getenv("CMBPO_NO_COMPACT");      // test switch: results must not depend on it
+    const bool compacting = cfg->precision != CMBPO_PREC_FP32 && !(no_compact && atoi(no_compact)) &&
                             (cfg->uncertainty_mode || cfg->env.term_id != CMBPO_TERM_NO_DONE);
     int cur_gen = 0;
     if (cmbpo_ws_get(ctx, 2, (size_t)dyn.E * B * 2 * dyn.D * sizeof(float), (void**)&raw)) return 1;

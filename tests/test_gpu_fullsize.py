@@ -234,3 +234,33 @@ def test_standalone_gae_config4(engine):
         g, gw = g.cpu().numpy()[sel], gw.cpu().numpy()[sel]
         assert np.array_equal(g, w)
         assert np.all(np.abs(gw - w) <= np.spacing(np.abs(w)) + 1e-30)
+
+
+def test_alive_row_compaction_is_invisible(engine, monkeypatch):
+    """Squeezing finished paths out of the batch (tensor-core path, AntSafe + uncertainty cut-off) must
+    not change a single bit: a row's result does not depend on which tile / lane it occupies."""
+    import cmbpo_b200 as cb
+    from cmbpo_b200 import _lib as L
+    task, O, A = TASKS["ant"]
+    B, T = 20000, 35
+    dyn, actor, v, vc = orc.make_problem(12, O, A, hidden=(512, 512), task=task)
+    load_problem(engine, dyn, actor, v, vc)
+    obs, act = orc.make_states(13, B, O, A, dyn)
+    lim = calibrated_dkl_lim(dyn, task, obs[:2000], act[:2000], factor=30.0)
+    cfg = L.EnvCfg(L.TERM_ANTSAFE, L.COST_ANTSAFE, 0, 1, 1)
+    t = engine.torch
+    res = []
+    for no_compact in ("0", "1"):
+        monkeypatch.setenv("CMBPO_NO_COMPACT", no_compact)
+        bufs = cb.RolloutBuffers(engine, B, T, O, A)
+        bufs.set_inputs(obs)
+        bufs.run(cfg, uncertainty_mode=True, dkl_lim=lim, seed=21, precision="fp16")
+        bufs.gae(GAE["gamma"], GAE["lam"], GAE["cost_gamma"], GAE["cost_lam"])
+        engine.synchronize()
+        res.append(bufs)
+    a, b = res
+    ln = a.length.cpu().numpy()
+    assert 4 < ln.mean() < T - 3 and len(np.unique(ln)) > 8       # paths really end at many different steps
+    for name in ("length", "end_reason", "last_val", "last_cval", "obs", "nextobs", "act", "mu", "rew", "val", "cval",
+                 "logp", "cost", "dkl", "dyn_error", "term", "adv", "ret", "cadv", "cret", "cum_dkl"):
+        assert bool(t.equal(getattr(a, name), getattr(b, name))), name
