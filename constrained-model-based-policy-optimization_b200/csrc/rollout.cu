@@ -595,6 +595,8 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
     const bool compacting = cfg->precision != CMBPO_PREC_FP32 && !(no_compact && atoi(no_compact)) &&
                             (cfg->uncertainty_mode || cfg->env.term_id != CMBPO_TERM_NO_DONE);
     int cur_gen = 0;
+    const char* ce = getenv("CMBPO_COMPACT_EVERY");           // experiment knob; default below
+    const int compact_every = (ce && atoi(ce) > 0) ? atoi(ce) : 4;
     if (cmbpo_ws_get(ctx, 2, (size_t)dyn.E * B * 2 * dyn.D * sizeof(float), (void**)&raw)) return 1;
 
     CUDA_TRY(cudaMemsetAsync(bufs->step_stats, 0, (size_t)T * 4 * sizeof(double), ctx->stream));
@@ -646,7 +648,7 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
             kern<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), STEP_THREADS, smem, ctx->stream>>>(sa);
         }
         ctx->launches++;
-        if (compacting && (t & 3) == 3 && t + 1 < n_steps) {
+        if (compacting && (t % compact_every) == compact_every - 1 && t + 1 < n_steps) {
             compact_flags_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, row_path[cur_gen], n_dev + cur_gen, alive, pending, cflags);
             ctx->launches++;
             if (cmbpo_path_offsets(ctx, cflags, B, coff)) return 1;
