@@ -72,6 +72,8 @@ extern "C" int cmbpo_ctx_destroy(cmbpo_ctx* ctx) {
     net_free(ctx->polnet);
     if (ctx->log_std) cudaFree(ctx->log_std);
     for (Workspace& w : ctx->ws) if (w.ptr) cudaFree(w.ptr);
+    if (ctx->host_n) cudaFreeHost(ctx->host_n);
+    for (cudaEvent_t e : ctx->n_ev) if (e) cudaEventDestroy(e);
     delete ctx;
     return 0;
 }

@@ -605,10 +605,24 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
     if (compacting) {
         compact_init_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, row_path[0], n_dev);
         ctx->launches++;
+        if (!ctx->host_n) {
+            CUDA_TRY(cudaHostAlloc((void**)&ctx->host_n, 4 * sizeof(int64_t), cudaHostAllocDefault));
+            for (cudaEvent_t& e : ctx->n_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
     }
+    // The live row count is mirrored to the host after every compaction; the host stays at most 3
+    // compactions (6 steps = 24 launches) ahead of the device and stops issuing steps once no path is
+    // alive or waiting for a bootstrap value (short rollouts in 'uncertainty' mode end long before the
+    // horizon, and 30 steps of empty launches cost more than the steps that did work).
+    int n_compactions = 0;
 
     for (int t = 0; t <= n_steps; ++t) {
         const bool last = (t == n_steps);
+        if (compacting && n_compactions >= 3) {
+            const int slot = (n_compactions - 3) & 3;          // the compaction three back
+            CUDA_TRY(cudaEventSynchronize(ctx->n_ev[slot]));
+            if (ctx->host_n[slot] == 0) break;                 // nothing alive, nothing pending
+        }
         PolicyRowsArgs pa = {};
         pa.N = B; pa.O = O; pa.A = A; pa.obs = cur;
         pa.row_path = compacting ? row_path[cur_gen] : nullptr;
@@ -658,6 +672,10 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
             ctx->launches++;
             std::swap(cur, cur2);
             cur_gen ^= 1;
+            const int slot = n_compactions & 3;
+            CUDA_TRY(cudaMemcpyAsync(ctx->host_n + slot, n_dev + cur_gen, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaEventRecord(ctx->n_ev[slot], ctx->stream));
+            ++n_compactions;
         }
     }
     rollout_final_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, O, cur, alive, *bufs, v, vc,
