@@ -697,6 +697,11 @@ bool ens_tc_supported(const Net& n) {
     const int hd = n.dims[1];
     if (n.dims[2] != hd || (hd != 128 && hd != 256 && hd != 512)) return false;
     if (n.dims[0] > 64 || n.dims[3] > 128) return false;
+    // KNOWN ISSUE: width 256 with a two-part output (more than 64 output columns) fails intermittently
+    // (launch failure) when a CTA processes several units; found by tools/soak.py, not yet understood
+    // (512- and 128-wide nets with the same output shape, and 256-wide nets with <= 64 outputs, pass
+    // every probe).  Refuse the shape instead of risking it.
+    if (hd == 256 && out_shape(n.dims[3]).parts == 2) return false;
     if (n.acts[0] != n.acts[1] || n.acts[2] != CMBPO_ACT_NONE) return false;
     return n.acts[0] == CMBPO_ACT_SWISH || n.acts[0] == CMBPO_ACT_TANH;
 }

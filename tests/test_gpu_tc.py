@@ -102,3 +102,19 @@ def test_rollout_tc_other_ensemble_shapes(engine, num_nets, hidden, B):
         err = np.max(np.abs(na[m, t] - nb[m, t]) / scale)
         assert err <= 3e-3 * (t + 1), (t, err)
         assert np.allclose(da[m, t], db[m, t], rtol=5e-2, atol=1e-4), t      # closed-form vs all-pairs KL, fp16 inputs
+
+
+def test_unsupported_tc_shape_fails_loudly(engine):
+    """Width 256 with more than 64 output columns is refused by the tcgen05 path (known issue, see
+    ens_tc_supported): a clear error, never a silent fallback."""
+    import cmbpo_b200 as cb
+    from cmbpo_b200 import _lib as L
+    task, O, A = TASKS["hum"]
+    dyn, actor, v, vc = orc.make_problem(99, O, A, hidden=(256, 256), task=task)
+    model, _ = load_problem(engine, dyn, actor, v, vc)
+    obs, act = orc.make_states(98, 300, O, A, dyn)
+    x = engine.to_device(np.concatenate([obs, act], -1))
+    with pytest.raises(cb.CmbpoError, match="tcgen05 path needs"):
+        model.predict_ensemble_device(x, precision="fp16")
+    m32 = model.predict_ensemble_device(x, precision="fp32")[0]      # the CUDA-core variant serves it
+    assert bool(engine.torch.isfinite(m32).all())
