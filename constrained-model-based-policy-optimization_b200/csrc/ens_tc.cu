@@ -290,10 +290,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         for (long long u = u0; u < u1; ++u) {
             int jin = 0;
             for (int jj = 0; jj < NC; ++jj) {
-                const uint32_t hb = (nh2 == 2) ? (c1 & 1) : 0, hn = (nh2 == 2) ? (c1 >> 1) : c1;
+                // barrier pair = chunk parity (one per epilogue pair), also when H2 is single buffered:
+                // every waiter then sees consecutive phases of "its" barrier and the parity test is exact
+                const uint32_t hbar = c1 & 1, hn = c1 >> 1, hb = (nh2 == 2) ? hbar : 0;
                 if (jin == 0) wait_t<DBG>(bar + W2_FULL + s2, ph2, c_w2);
                 if (jj == 0) wait_t<DBG>(bar + OUT_EMPTY, (m & 1) ^ 1, c_out);
-                wait_t<DBG>(bar + H2_FULL + hb, hn & 1, c_h2);
+                wait_t<DBG>(bar + H2_FULL + hbar, hn & 1, c_h2);
                 tc_fence_after();
                 const bool last_in_slot = (jin == p.cps - 1) || (jj == NC - 1);
                 if (elect_one()) {
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                             mma_f16_ts(tmem + col_out + (jj / CPM) * p.NP + q * NPp, tmem + COL_H2 + hb * 32 + ks * 8,
                                        dB + 2 * ks, idesc_o, !(jj % CPM == 0 && ks == 0));
                     }
-                    mma_commit(bar + H2_EMPTY + hb);
+                    mma_commit(bar + H2_EMPTY + hbar);
                     if (last_in_slot) mma_commit(bar + W2_EMPTY + s2);
                     if (jj == NC - 1) mma_commit(bar + OUT_FULL);
                 }
@@ -535,7 +537,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 for (int i = 0; i < NC / 2; ++i) {               // layer-1 chunk j -> an H2 buffer
                     const int j = 2 * i + (int)pair;
                     const uint32_t gg = g + j, buf = pair, n = gg >> 1, cc = c1 + j;
-                    const uint32_t hb = (nh2 == 2) ? (cc & 1) : 0, hn = (nh2 == 2) ? (cc >> 1) : cc;
+                    // H2 hand-off.  Double buffered: wait until the partial of chunk cc-2 (same buffer, same
+                    // barrier, previous phase) has read it.  Single buffered: wait for the partial of chunk
+                    // cc-1, which signals the OTHER pair's barrier (phase (cc-1)/2).  A single barrier shared
+                    // by both pairs is wrong: a pair that is a whole phase ahead of the layer-2 issuer passes
+                    // the parity test of the phase before (seen as an intermittent dead-lock with 256-wide
+                    // nets and two-part outputs).
+                    const uint32_t hbar = cc & 1, hn = cc >> 1, hb = (nh2 == 2) ? hbar : 0;
+                    uint64_t* h2_free = (nh2 == 2) ? bar + H2_EMPTY + hbar : (cc == 0 ? nullptr : bar + H2_EMPTY + (hbar ^ 1));
+                    const uint32_t h2_par = (nh2 == 2) ? ((hn & 1) ^ 1) : ((((cc - 1) >> 1)) & 1);
                     const float bias_lane = bias_next;
                     if (i + 1 < NC / 2) bias_next = __ldg(bias + HD + (j + 2) * 64 + half * 32 + lane);
                     wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
@@ -544,10 +554,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     const long long td = (DBG && g_tc_count_waits) ? clock64() : 0;
                     drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
                                       tmem + COL_H2 + hb * 32 + half * 16 + lane_base, bar + D_EMPTY + buf,
-                                      bar + H2_EMPTY + hb, (hn & 1) ^ 1);
+                                      h2_free, h2_par);
                     if (DBG && g_tc_count_waits) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar + H2_FULL + hb);
+                    if (lane == 0) mbar_arrive(bar + H2_FULL + hbar);
                     if (half == 0) { TRACE(1 + pair, 2100 + j); }
                 }
                 g += NC; c1 += NC;
@@ -697,11 +707,6 @@ bool ens_tc_supported(const Net& n) {
     const int hd = n.dims[1];
     if (n.dims[2] != hd || (hd != 128 && hd != 256 && hd != 512)) return false;
     if (n.dims[0] > 64 || n.dims[3] > 128) return false;
-    // KNOWN ISSUE: width 256 with a two-part output (more than 64 output columns) fails intermittently
-    // (launch failure) when a CTA processes several units; found by tools/soak.py, not yet understood
-    // (512- and 128-wide nets with the same output shape, and 256-wide nets with <= 64 outputs, pass
-    // every probe).  Refuse the shape instead of risking it.
-    if (hd == 256 && out_shape(n.dims[3]).parts == 2) return false;
     if (n.acts[0] != n.acts[1] || n.acts[2] != CMBPO_ACT_NONE) return false;
     return n.acts[0] == CMBPO_ACT_SWISH || n.acts[0] == CMBPO_ACT_TANH;
 }

@@ -18,9 +18,6 @@ for it in range(12):
     E = int(rng.choice([3, 5, 7]))
     dyn, actor, v, vc = wl.make_problem(it, O, A, hidden=hidden, num_nets=E, num_elites=max(1, E - 2), task=task)
     prec = ["fp16", "bf16"][it % 2]
-    if hidden == (256, 256) and 2 * (O + 1) > 64:
-        hidden = (512, 512)        # width 256 with > 64 outputs is refused by the tcgen05 path (known issue)
-        dyn, actor, v, vc = wl.make_problem(it, O, A, hidden=hidden, num_nets=E, num_elites=max(1, E - 2), task=task)
     eng = cb.Engine(0, precision=prec)
     cb.B200PE.from_oracle_ensemble(eng, L.NET_DYN, dyn)
     pol = cb.B200Policy(eng); pol.load_actor(actor.W, actor.b, actor.log_std); pol.load_values(v, vc)
