@@ -166,7 +166,7 @@ typedef struct {
     uint8_t* end_reason;         /* [B] CMBPO_END_* */
     float *last_val, *last_cval; /* [B] bootstrap values for the GAE pass */
     double *cum_dkl, *path_return, *path_cost; /* [B] float64 accumulators, model_sampler.py:218-226 */
-    float* final_obs;            /* [B,O] observation each path stopped at */
+    float* final_obs;            /* [B,O] current observation of every path still alive at the end */
     double* step_stats;          /* [T,4] per step: rows fed to the model, sum of dkl_path over them,
                                     rows stored, sum of ensemble_ep_var over the stored rows */
 } cmbpo_rollout_bufs;
@@ -183,6 +183,10 @@ typedef struct {
     cmbpo_env_cfg env;
 } cmbpo_rollout_cfg;
 
+/* Like the reference (model_sampler.py:255-259, 300-311) only alive paths are fed to the networks: on
+ * the tensor-core precisions, where paths can end early (termination function / uncertainty mode), the
+ * rows of finished paths are compacted out of the batch on the device every other step; results do
+ * not depend on it (bit-identical).  final_obs is written for the paths still alive at the end. */
 int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const cmbpo_rollout_bufs* bufs);
 
 /*
