@@ -41,7 +41,11 @@ class RolloutBufs(C.Structure):
 class RolloutCfg(C.Structure):
     _fields_ = [("B", C.c_int64), ("path_id_base", C.c_int64), ("T", C.c_int),
                 ("max_steps", C.c_int), ("uncertainty_mode", C.c_int), ("dkl_lim", C.c_double),
-                ("seed", C.c_uint64), ("precision", C.c_int), ("env", EnvCfg)]
+                ("seed", C.c_uint64), ("precision", C.c_int), ("env", EnvCfg),
+                ("flags", C.c_int), ("compact_every", C.c_int)]
+
+
+ROLLOUT_NO_COMPACT, ROLLOUT_NO_FUSE, ROLLOUT_NO_STORE = 1, 2, 4
 
 
 # name -> (restype, argtypes); every symbol include/cmbpo_b200.h declares
@@ -86,6 +90,7 @@ SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 2
 
 
 class CmbpoError(RuntimeError):
@@ -105,7 +110,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.cmbpo_abi_version() != 1:
+    if lib.cmbpo_abi_version() != ABI_VERSION:
         raise CmbpoError("ABI version mismatch")
     _lib = lib
     return lib

@@ -12,25 +12,9 @@
 #include <cstring>
 #include "common.cuh"
 #include "row_math.cuh"
+#include "step_common.cuh"
 
 namespace {
-
-struct ValueHead {            // one non-probabilistic value ensemble read through PE.predict
-    const float* raw;         // [E, N, ld], value in column 0
-    int E, ld;
-    const float *mu_out, *sig_out;   // [1] or null
-};
-
-__device__ __forceinline__ float value_of(const ValueHead& h, int64_t N, int64_t p) {
-    // tf.reduce_mean over members of inverse_transform(out) (pe.py:343, pens/utils.py:167)
-    float s = 0.f;
-    for (int e = 0; e < h.E; ++e) {
-        float m = h.raw[((int64_t)e * N + p) * h.ld];
-        if (h.mu_out) m = __fadd_rn(__fmul_rn(h.sig_out[0], m), h.mu_out[0]);
-        s = (e == 0) ? m : __fadd_rn(s, m);
-    }
-    return __fdiv_rn(s, (float)h.E);
-}
 
 struct PolicyRowsArgs {
     int64_t N;                 // rows
@@ -61,6 +45,7 @@ constexpr int POLICY_ROWS = 128;      // rows (= threads) per block of policy_ro
 // all threads: the block's [128, O+A] slice of the dynamics input `xin` = concat(obs, pi) is one
 // contiguous range -> written with consecutive threads on consecutive floats (a per-row loop writes
 // 32 different 128-byte lines per store instruction).
+template <bool FAST>
 __global__ void __launch_bounds__(POLICY_ROWS) policy_rows_kernel(PolicyRowsArgs a) {
     __shared__ float s_pi[POLICY_ROWS * CMBPO_MAX_ACT];
     __shared__ unsigned char s_live[POLICY_ROWS];
@@ -86,20 +71,11 @@ __global__ void __launch_bounds__(POLICY_ROWS) policy_rows_kernel(PolicyRowsArgs
         }
         live = live && a.mu_raw;
         if (live) {
-            float mu[CMBPO_MAX_ACT], eps[CMBPO_MAX_ACT], pi[CMBPO_MAX_ACT];
             const int64_t gid = a.path_ids ? (int64_t)a.path_ids[r] : a.path_base + p;
-            if (!a.eps) philox_normals(a.seed, gid, a.step, RNG_STREAM_ACT, a.A, eps);
-            for (int i = 0; i < a.A; ++i) {
-                mu[i] = a.mu_raw[r * a.A + i];
-                if (a.eps) eps[i] = a.eps[p * a.A + i];
-            }
-            float lp = actor_row(mu, a.log_std, eps, a.A, pi);
+            const float lp = policy_head_row<FAST>(a.mu_raw + r * a.A, a.log_std, a.eps ? a.eps + p * a.A : nullptr,
+                                                   a.seed, gid, a.step, a.A, a.pi ? a.pi + r * a.A : nullptr,
+                                                   a.mu ? a.mu + r * a.A : nullptr, s_pi + threadIdx.x * a.A);
             if (a.logp) a.logp[r] = lp;
-            for (int i = 0; i < a.A; ++i) {
-                if (a.pi) a.pi[r * a.A + i] = pi[i];
-                if (a.mu) a.mu[r * a.A + i] = mu[i];
-                s_pi[threadIdx.x * a.A + i] = pi[i];
-            }
         }
     }
     s_live[threadIdx.x] = live ? 1 : 0;
@@ -199,14 +175,13 @@ __global__ void finish_mean_kernel(const double* sum, int64_t n, float* out) {
 
 // ---- rollout step ------------------------------------------------------------------------
 struct StepArgs {
-    int64_t B; int O, A, T, t; int last_storable;   // last_storable = T-2: storing it ends the path (horizon)
+    StepRules rules;         // B, t, horizon / uncertainty rules, alive / pending flags, the buffers
+    int64_t B; int O, A, T, t;
     EnvRowCfg c; int n_elite;
-    int uncertainty; double dkl_lim;
     int64_t path_base; uint64_t seed;
     const float* raw;        // [E,B,2D]
     float* cur_obs;          // [B,O] in/out
     uint8_t* alive;          // [B]
-    uint8_t* pending;        // [B]
     const float *pi, *mu, *logp, *v, *vc;      // this step's policy outputs [B,..]
     const int32_t* elite_pos;                  // [B] slice for this step or null (indexed by path)
     const float* state_eps;                    // [B,O] slice or null (indexed by path)
@@ -308,34 +283,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs 
             RawStaged raw(s_raw, rows, W, r);
             const EnvRowOut o = env_row_finish<FAST>(a.c, raw, s_member[r], s_kl + r * O, s_epv + r * O, s_nx + r * O,
                                                s_fin + r * O);
-            const float v = pf_v, vc = pf_vc;
-            // uncertainty cut-off BEFORE the step is stored (model_sampler.py:275-290)
-            const double next_dkl = pf_dkl + (double)o.dkl_path;
-            const bool cut = a.uncertainty && next_dkl >= a.dkl_lim;
-            st0 += 1.0; st1 += (double)o.dkl_path;
-            if (cut) {
-                s_state[r] = 2;
-                a.alive[p] = 0;
-                a.b.end_reason[p] = CMBPO_END_UNCERTAIN;
-                a.b.last_val[p] = v; a.b.last_cval[p] = vc;      // V(s_t), VC(s_t): model_sampler.py:401-407
-            } else {
-                s_state[r] = 1;
-                const int64_t row = (int64_t)t * a.B + p;          // ModelBuffer.store_multiple, time-major
-                a.b.rew[row] = o.rew; a.b.val[row] = v; a.b.cost[row] = o.cost; a.b.cval[row] = vc;
-                a.b.logp[row] = pf_logp; a.b.dyn_error[row] = o.ep_var_mean; a.b.dkl[row] = o.dkl_path;
-                a.b.term[row] = o.term ? 1 : 0;
-                a.b.length[p] = t + 1;
-                a.b.cum_dkl[p] = next_dkl;                        // model_sampler.py:332
-                a.b.path_return[p] = pf_ret + (double)o.rew;      // :317-318
-                a.b.path_cost[p] = pf_cost + (double)o.cost;
-                st2 += 1.0; st3 += (double)o.ep_var_sum;
-                if (t >= a.last_storable) {                       // path_length >= max_path_length-1 (:352)
-                    a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_HORIZON; a.pending[p] = 3;
-                } else if (o.term) {                              // env terminal (:357-364)
-                    a.alive[p] = 0; a.b.end_reason[p] = CMBPO_END_TERMINAL;
-                    a.b.last_val[p] = 0.f; a.pending[p] = 2;
-                }
-            }
+            RowCarry pf;
+            pf.v = pf_v; pf.vc = pf_vc; pf.logp = pf_logp; pf.dkl = pf_dkl; pf.ret = pf_ret; pf.cost = pf_cost;
+            s_state[r] = (unsigned char)step_row_commit(a.rules, p, o, pf, st0, st1, st2, st3);
         }
         __syncthreads();
         for (int idx = threadIdx.x; idx < NI; idx += STEP_THREADS) {
@@ -343,10 +293,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 4) rollout_step_kernel(StepArgs 
             if (s_state[r] != 1) continue;
             const int64_t p = s_path[r], row = (int64_t)t * a.B + p;
             const float nx = s_nx[idx];
-            a.b.obs[row * O + dim] = a.cur_obs[(base + r) * O + dim];
-            a.b.nextobs[row * O + dim] = nx;
+            if (!a.rules.no_store) {
+                a.b.obs[row * O + dim] = a.cur_obs[(base + r) * O + dim];
+                a.b.nextobs[row * O + dim] = nx;
+            }
             a.cur_obs[(base + r) * O + dim] = nx;                 // model_sampler.py:350
         }
+        if (!a.rules.no_store)
         for (int idx = threadIdx.x; idx < rows * A; idx += STEP_THREADS) {
             const int r = idx / A, i = idx - r * A;
             if (s_state[r] != 1) continue;
@@ -476,7 +429,7 @@ int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precis
         a.log_std = ctx->log_std;
         a.v = make_head(v, raw + (size_t)a.N * A); a.v.ld = A;
         a.vc = make_head(vc, raw + (size_t)(1 + v.E) * a.N * A); a.vc.ld = A;
-        policy_rows_kernel<<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
+        policy_rows_kernel<true><<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -497,7 +450,8 @@ int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precis
     }
     a.mu_raw = raw_mu; a.log_std = ctx->log_std;
     a.v = make_head(v, raw_v); a.vc = make_head(vc, raw_vc);
-    policy_rows_kernel<<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
+    if (precision != CMBPO_PREC_FP32) policy_rows_kernel<true><<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
+    else policy_rows_kernel<false><<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -591,12 +545,25 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
     alive = (uint8_t*)(cflags + B); pending = alive + B;
     // alive-row compaction: only where paths can end before the horizon, and only on the tcgen05 path
     // (the fp32 GEMM kernels take their row count from the host)
-    const char* no_compact = getenv("CMBPO_NO_COMPACT");      // test switch: results must not depend on it
-    const bool compacting = cfg->precision != CMBPO_PREC_FP32 && !(no_compact && atoi(no_compact)) &&
+    const bool compacting = cfg->precision != CMBPO_PREC_FP32 && !(cfg->flags & CMBPO_ROLLOUT_NO_COMPACT) &&
                             (cfg->uncertainty_mode || cfg->env.term_id != CMBPO_TERM_NO_DONE);
     int cur_gen = 0;
-    const char* ce = getenv("CMBPO_COMPACT_EVERY");           // experiment knob; default below
-    const int compact_every = (ce && atoi(ce) > 0) ? atoi(ce) : 2;    // measured: 2 beats 1 and 4 by 2-6 %
+    const int compact_every = cfg->compact_every > 0 ? cfg->compact_every : 2;    // measured: 2 beats 1 and 4 by 2-6 %
+    // Fused step (tcgen05 precisions): policy head in the dynamics kernel's input staging, FakeEnv row math /
+    // sampler rules / ModelBuffer write-out in its epilogue -> two launches per step, and the raw [E,B,2D]
+    // outputs only exist tile by tile in an L2-resident scratch.
+    const int rp_shift = ens_tc_fused_rp_shift(O);
+    const bool fused = cfg->precision != CMBPO_PREC_FP32 && !(cfg->flags & CMBPO_ROLLOUT_NO_FUSE) && ctx->polnet.loaded &&
+                       ens_tc_fusable(dyn) && rp_shift >= 5 && dyn.n_elite <= 8 && A <= CMBPO_MAX_ACT;
+    const int64_t ntiles = (B + 127) / 128;
+    int* tile_cnt = nullptr;
+    float* pol_raw = nullptr;
+    if (fused) {
+        if (cmbpo_ws_get(ctx, 7, (size_t)ntiles * sizeof(int), (void**)&tile_cnt)) return 1;
+        CUDA_TRY(cudaMemsetAsync(tile_cnt, 0, (size_t)ntiles * sizeof(int), ctx->stream));
+        if (cmbpo_ws_get(ctx, 2, (size_t)ntiles * 128 * dyn.E * 2 * dyn.D * sizeof(float), (void**)&raw)) return 1;
+        if (cmbpo_ws_get(ctx, 3, (size_t)ctx->polnet.E * B * A * sizeof(float), (void**)&pol_raw)) return 1;
+    } else
     if (cmbpo_ws_get(ctx, 2, (size_t)dyn.E * B * 2 * dyn.D * sizeof(float), (void**)&raw)) return 1;
 
     CUDA_TRY(cudaMemsetAsync(bufs->step_stats, 0, (size_t)T * 4 * sizeof(double), ctx->stream));
@@ -623,6 +590,36 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
             CUDA_TRY(cudaEventSynchronize(ctx->n_ev[slot]));
             if (ctx->host_n[slot] == 0) break;                 // nothing alive, nothing pending
         }
+        if (fused && !last) {
+            const int64_t* nd = compacting ? n_dev + cur_gen : nullptr;
+            {
+                ProfScope prof(ctx, CMBPO_PROF_POLICY);
+                if (ens_forward(ctx, ctx->polnet, cur, B, false, pol_raw, cfg->precision, nd)) return 1;
+            }
+            FusedStep fz = {};
+            fz.rules.B = B; fz.rules.t = t; fz.rules.last_storable = T - 2;
+            fz.rules.uncertainty = cfg->uncertainty_mode; fz.rules.dkl_lim = cfg->dkl_lim;
+            fz.rules.alive = alive; fz.rules.pending = pending; fz.rules.b = *bufs;
+            fz.rules.no_store = (cfg->flags & CMBPO_ROLLOUT_NO_STORE) ? 1 : 0;
+            fz.O = O; fz.A = A; fz.n_elite = dyn.n_elite;
+            fz.c = make_env_cfg(dyn, cfg->env, O, cfg->precision);
+            fz.path_base = cfg->path_id_base; fz.seed = cfg->seed;
+            fz.cur_obs = cur; fz.pol_raw = pol_raw;
+            fz.v = make_head(ctx->nets[CMBPO_NET_V], pol_raw + (size_t)B * A); fz.v.ld = A;
+            fz.vc = make_head(ctx->nets[CMBPO_NET_VC], pol_raw + (size_t)(1 + ctx->nets[CMBPO_NET_V].E) * B * A); fz.vc.ld = A;
+            fz.log_std = ctx->log_std;
+            fz.pi = pi; fz.mu = mu; fz.logp = logp; fz.vrow = v; fz.vcrow = vc;
+            fz.act_eps = bufs->act_eps ? bufs->act_eps + (size_t)t * B * A : nullptr;
+            fz.elite_pos = bufs->elite_pos ? bufs->elite_pos + (size_t)t * B : nullptr;
+            fz.state_eps = bufs->state_eps ? bufs->state_eps + (size_t)t * B * O : nullptr;
+            fz.row_path = compacting ? row_path[cur_gen] : nullptr;
+            fz.raw_tiles = raw; fz.tile_cnt = tile_cnt; fz.rp_shift = rp_shift;
+            { const char* sk = getenv("CMBPO_FZ_SKIP"); fz.dbg_skip = sk ? atoi(sk) : 0; }   // TEMP probe
+            {
+                ProfScope prof(ctx, CMBPO_PROF_DYN);
+                if (ens_forward_tc(ctx, dyn, nullptr, B, nullptr, cfg->precision, nd, &fz)) return 1;
+            }
+        } else {
         PolicyRowsArgs pa = {};
         pa.N = B; pa.O = O; pa.A = A; pa.obs = cur;
         pa.row_path = compacting ? row_path[cur_gen] : nullptr;
@@ -639,11 +636,14 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
         if (ens_forward(ctx, dyn, xin, B, false, raw, cfg->precision, pa.n_dev)) return 1;
         StepArgs sa = {};
         sa.row_path = pa.row_path; sa.n_dev = pa.n_dev;
-        sa.B = B; sa.O = O; sa.A = A; sa.T = T; sa.t = t; sa.last_storable = T - 2;
+        sa.B = B; sa.O = O; sa.A = A; sa.T = T; sa.t = t;
         sa.c = make_env_cfg(dyn, cfg->env, O, cfg->precision); sa.n_elite = dyn.n_elite;
-        sa.uncertainty = cfg->uncertainty_mode; sa.dkl_lim = cfg->dkl_lim;
+        sa.rules.B = B; sa.rules.t = t; sa.rules.last_storable = T - 2;
+        sa.rules.uncertainty = cfg->uncertainty_mode; sa.rules.dkl_lim = cfg->dkl_lim;
+        sa.rules.alive = alive; sa.rules.pending = pending; sa.rules.b = *bufs;
+        sa.rules.no_store = (cfg->flags & CMBPO_ROLLOUT_NO_STORE) ? 1 : 0;
         sa.path_base = cfg->path_id_base; sa.seed = cfg->seed;
-        sa.raw = raw; sa.cur_obs = cur; sa.alive = alive; sa.pending = pending;
+        sa.raw = raw; sa.cur_obs = cur; sa.alive = alive;
         sa.pi = pi; sa.mu = mu; sa.logp = logp; sa.v = v; sa.vc = vc;
         sa.elite_pos = bufs->elite_pos ? bufs->elite_pos + (size_t)t * B : nullptr;
         sa.state_eps = bufs->state_eps ? bufs->state_eps + (size_t)t * B * O : nullptr;
@@ -662,6 +662,7 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
             kern<<<(unsigned)std::min<int64_t>(cdiv(B, step_rows(O)), (int64_t)ctx->sm_count * 64), STEP_THREADS, smem, ctx->stream>>>(sa);
         }
         ctx->launches++;
+        }   // step-wise path
         if (compacting && (t % compact_every) == compact_every - 1 && t + 1 < n_steps) {
             compact_flags_kernel<<<cdiv(B, 256), 256, 0, ctx->stream>>>(B, row_path[cur_gen], n_dev + cur_gen, alive, pending, cflags);
             ctx->launches++;

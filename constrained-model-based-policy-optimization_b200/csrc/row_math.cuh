@@ -106,6 +106,55 @@ __device__ inline float np_sum_f32(const float (&a)[MAXN], int n) {
     return s;
 }
 
+// The same sum over a strided array (element i at a[i * stride]); used by the fused step kernel,
+// whose staging is [dim][row].
+__device__ inline float np_sum_strided(const float* a, int n, int stride) {
+    if (n < 8) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, a[i * stride]);
+        return s;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j * stride];
+    int i = 8;
+    for (; i < n - (n & 7); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[(i + j) * stride]);
+    }
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) s = __fadd_rn(s, a[i * stride]);
+    return s;
+}
+
+// Streaming form of the same order: elements arrive one by one (i = 0 .. n-1), the partial sums stay
+// in registers (all indices static after unrolling), so a per-row loop needs no local-memory array.
+struct NpSumStream {
+    float r[8], s;
+    int n, nb;                       // nb = n - n % 8: elements before the sequential tail
+    __device__ explicit NpSumStream(int n_) : s(0.f), n(n_), nb(n_ - (n_ & 7)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = 0.f;
+    }
+    __device__ __forceinline__ void tree() {
+        s = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                      __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    }
+    __device__ __forceinline__ void add(int i, float x) {
+        if (n < 8) { s = __fadd_rn(s, x); return; }
+        if (i < nb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if ((i & 7) == j) r[j] = (i < 8) ? x : __fadd_rn(r[j], x);
+            if (i == nb - 1) tree();
+        } else {
+            s = __fadd_rn(s, x);
+        }
+    }
+    __device__ __forceinline__ float result() const { return s; }
+};
+
 // ------------------------------------------------------------------------------------------
 // FakeEnv.step for one row (fake_env.py:104-153) given the raw last-layer outputs of all E
 // members.  `raw(e, c)` returns column c of member e for this row (c < 2*D).
@@ -128,20 +177,18 @@ struct EnvRowOut {
 // ------------------------------------------------------------------------------------------
 // Gaussian actor head for one row (ac_network.py:105-111, 46-48)
 // ------------------------------------------------------------------------------------------
-template <int MAXA>
-__device__ inline float actor_row(const float (&mu)[MAXA], const float* log_std, const float (&eps)[MAXA],
-                                  int A, float (&pi)[MAXA]) {
-    float terms[MAXA];
+// One action dimension: pi = mu + eps * exp(log_std) (ac_network.py:109) and its log-likelihood term
+// (ac_network.py:47).  FAST (tensor-core precision modes): approximate division (2 ulp) -- the IEEE
+// division is a subroutine call, which the fused tcgen05 kernel cannot afford in its epilogue warps.
+template <bool FAST>
+__device__ __forceinline__ float actor_dim(float mu, float ls, float eps, float& pi) {
     const float log2pi = 1.8378770664093453f;   // float32(np.log(2*np.pi))
-    for (int a = 0; a < A; ++a) {
-        float ls = log_std[a];
-        float sd = expf(ls);
-        pi[a] = __fadd_rn(mu[a], __fmul_rn(eps[a], sd));                         // ac_network.py:109
-        float z = __fdiv_rn(__fsub_rn(pi[a], mu[a]), __fadd_rn(sd, 1e-8f));
-        float t = __fadd_rn(__fadd_rn(__fmul_rn(z, z), __fmul_rn(2.0f, ls)), log2pi);
-        terms[a] = __fmul_rn(-0.5f, t);                                          // ac_network.py:47
-    }
-    return np_sum_f32(terms, A);
+    const float sd = expf(ls);
+    pi = __fadd_rn(mu, __fmul_rn(eps, sd));
+    const float num = __fsub_rn(pi, mu), den = __fadd_rn(sd, 1e-8f);
+    const float z = FAST ? __fdividef(num, den) : __fdiv_rn(num, den);
+    const float t = __fadd_rn(__fadd_rn(__fmul_rn(z, z), __fmul_rn(2.0f, ls)), log2pi);
+    return __fmul_rn(-0.5f, t);
 }
 
 // numpy pairwise-sum order over an array in memory (see np_sum_f32)
@@ -199,7 +246,7 @@ __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int 
             const float mean = __fadd_rn(__fmul_rn(sg, raw.load(pm)), mu);        // pe.py:815-821
             const float logvar = __fadd_rn(l2s, raw.load(pv));                    // pe.py:826-828
             pm += es; pv += es;
-            const float var = __expf(logvar);                                    // pe.py:833
+            const float var = FAST ? __expf(logvar) : expf(logvar);               // pe.py:833
             float x = mean;
             if (!c.deterministic) {                                              // fake_env.py:104-106
                 // FAST: var * rsqrt(var) (2 ulp) -- the IEEE square root is a subroutine call
@@ -213,7 +260,7 @@ __device__ __forceinline__ EnvDimOut env_dim_t(const EnvRowCfg& c, Raw raw, int 
             else if (isinf(var)) { l = 1e8f; }                                   // clip at 1e8 -> exp(2e8) = inf
             if (logvar != logvar) { l = logvar; v2 = logvar; }
             ls[e] = l; vr[e] = v2;
-            rv[e] = __fdividef(1.0f, __fadd_rn(v2, 1e-10f));
+            rv[e] = FAST ? __fdividef(1.0f, __fadd_rn(v2, 1e-10f)) : __fdiv_rn(1.0f, __fadd_rn(v2, 1e-10f));
             if (e == member) sel = x;
         }
     }
@@ -282,30 +329,42 @@ __device__ __forceinline__ EnvDimOut env_dim(const EnvRowCfg& c, Raw raw, int o,
     return env_dim_t<EC, FAST>(c, raw, o, member, obs_o, eps);
 }
 
-// row-owner part: ordered reductions over the O dimensions (numpy order), statics, reward
+// next state of ONE dimension from the chosen member only -- the same operations, in the same order,
+// as the `sel` / `nx` values of env_dim_t (the fused step kernel recomputes it at write-out time instead
+// of staging all of next_obs)
 template <bool FAST, class Raw>
-__device__ inline EnvRowOut env_row_finish(const EnvRowCfg& c, Raw raw, int member, const float* kl,
-                                           const float* epv, const float* nx, const unsigned char* fin) {
+__device__ __forceinline__ float env_dim_nx(const EnvRowCfg& c, Raw raw, int o, int member, float obs_o, float eps) {
+    const float mean = __fadd_rn(__fmul_rn(c.sig_out[o], raw(member, o)), c.mu_out[o]);
+    float x = mean;
+    if (!c.deterministic) {
+        const float logvar = __fadd_rn(c.l2s_out[o], raw(member, c.D + o));
+        const float var = FAST ? __expf(logvar) : expf(logvar);
+        const float sd = FAST ? ((var > 0.f && !isinf(var)) ? __fmul_rn(var, rsqrtf(var)) : var) : sqrtf(var);
+        x = __fadd_rn(mean, __fmul_rn(sd, eps));
+    }
+    return c.predicts_delta ? __fadd_rn(x, obs_o) : x;
+}
+
+// row-owner part: statics and reward from the reduced sums and the few next-state coordinates the
+// statics read (z = nx[0], q1 = nx[2], q2 = nx[3], last = nx[O-1])
+template <bool FAST, class Raw>
+__device__ __forceinline__ EnvRowOut env_row_core(const EnvRowCfg& c, Raw raw, int member, float ks, float es,
+                                                  bool all_finite, float z, float q1, float q2, float last) {
     const int O = c.O;
     EnvRowOut r;
-    const float ks = np_sum_ptr(kl, O);
     r.dkl_path = FAST ? __fdividef(ks, (float)O) : __fdiv_rn(ks, (float)O);      // fake_env.py:113
-    const float es = np_sum_ptr(epv, O);
     r.ep_var_sum = es;
     r.ep_var_mean = FAST ? __fdividef(es, (float)O) : __fdiv_rn(es, (float)O);   // model_sampler.py:343
-    bool all_finite = true;
-    for (int o = 0; o < O; ++o) all_finite = all_finite && fin[o];
     auto notdone = [&]() {                                                       // statics.py:24-27
-        const float z = nx[0], q1 = nx[2], q2 = nx[3];
         const float zrot = __fsub_rn(1.0f, __fmul_rn(2.0f, __fadd_rn(__fmul_rn(q1, q1), __fmul_rn(q2, q2))));
         const bool flags = all_finite && (z >= 0.2f) && (z <= 1.0f);
         return __fmul_rn(flags ? 1.0f : 0.0f, zrot) >= -0.7f;
     };
     r.term = (c.term_id == CMBPO_TERM_ANTSAFE) ? !notdone() : false;             // statics.py:17-31
     if (c.cost_id == CMBPO_COST_HCS) {                                           // statics.py:10-15
-        r.cost = (fabsf(__fmul_rn(nx[O - 1], 10.0f)) < 2.0f) ? 1.0f : 0.0f;
+        r.cost = (fabsf(__fmul_rn(last, 10.0f)) < 2.0f) ? 1.0f : 0.0f;
     } else if (c.cost_id == CMBPO_COST_ANTSAFE) {                                // statics.py:33-53
-        const float cc = (!notdone() ? 1.0f : 0.0f) + ((fabsf(nx[O - 1]) > 3.2f) ? 1.0f : 0.0f);
+        const float cc = (!notdone() ? 1.0f : 0.0f) + ((fabsf(last) > 3.2f) ? 1.0f : 0.0f);
         r.cost = fminf(fmaxf(cc, 0.0f), 1.0f);
     } else {
         r.cost = 0.0f;                                                           // fake_env.py:146
@@ -317,4 +376,17 @@ __device__ inline EnvRowOut env_row_finish(const EnvRowCfg& c, Raw raw, int memb
     }
     r.rew = __fadd_rn(__fmul_rn(c.sig_out[rcol], raw(member, rcol)), c.mu_out[rcol]);   // :148-151
     return r;
+}
+
+// ordered reductions over the O dimensions (numpy order) from per-dimension arrays, then the core
+template <bool FAST, class Raw>
+__device__ inline EnvRowOut env_row_finish(const EnvRowCfg& c, Raw raw, int member, const float* kl,
+                                           const float* epv, const float* nx, const unsigned char* fin) {
+    const int O = c.O;
+    const float ks = np_sum_ptr(kl, O);
+    const float es = np_sum_ptr(epv, O);
+    bool all_finite = true;
+    for (int o = 0; o < O; ++o) all_finite = all_finite && fin[o];
+    return env_row_core<FAST>(c, raw, member, ks, es, all_finite, nx[0], O > 2 ? nx[2] : 0.f, O > 3 ? nx[3] : 0.f,
+                              nx[O - 1]);
 }

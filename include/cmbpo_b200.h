@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CMBPO_ABI_VERSION 1
+#define CMBPO_ABI_VERSION 2
 
 typedef struct cmbpo_ctx cmbpo_ctx;
 
@@ -181,12 +181,29 @@ typedef struct {
     uint64_t seed;
     int precision;
     cmbpo_env_cfg env;
+    int flags;                   /* CMBPO_ROLLOUT_* bits (ABI 2) */
+    int compact_every;           /* steps between alive-row compactions; <= 0 -> 2 (ABI 2) */
 } cmbpo_rollout_cfg;
+
+/* cmbpo_rollout_cfg.flags.  None of them changes a result bit (tests compare both settings):
+ *   NO_COMPACT  keep finished paths' rows in the batch (see below);
+ *   NO_FUSE     tensor-core precisions: run the step as separate launches (policy GEMM, policy rows,
+ *               dynamics GEMM with raw [E,B,2D] outputs in HBM, row kernel) instead of the fused step
+ *               kernel (policy head in the dynamics kernel's input staging, FakeEnv / sampler rules /
+ *               ModelBuffer write-out in its epilogue);
+ *   NO_STORE    do not write the per-step ModelBuffer fields (obs .. term may then be NULL): only the
+ *               per-path results and step_stats -- ModelSampler.compute_dynamics_dkl
+ *               (samplers/model_sampler.py:151-167) = sum_t step_stats[t][1] / sum_t step_stats[t][0]. */
+enum { CMBPO_ROLLOUT_NO_COMPACT = 1, CMBPO_ROLLOUT_NO_FUSE = 2, CMBPO_ROLLOUT_NO_STORE = 4 };
 
 /* Like the reference (model_sampler.py:255-259, 300-311) only alive paths are fed to the networks: on
  * the tensor-core precisions, where paths can end early (termination function / uncertainty mode), the
  * rows of finished paths are compacted out of the batch on the device every other step; results do
- * not depend on it (bit-identical).  final_obs is written for the paths still alive at the end. */
+ * not depend on it (bit-identical).  final_obs is written for the paths still alive at the end.
+ * Host synchronisation: none without compaction.  With compaction the live row count is mirrored to the
+ * host after every compaction and the call waits (cudaEventSynchronize) for the count of the compaction
+ * THREE back before issuing further steps, so that it can stop once no path is alive; the call therefore
+ * returns at most 3 compactions ahead of the device. */
 int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const cmbpo_rollout_bufs* bufs);
 
 /*

@@ -25,14 +25,14 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(lib, n), "missing export %s" % n
         assert n in _lib.SIGNATURES, "no ctypes prototype for %s" % n
     assert sorted(_lib.SIGNATURES) == names
-    assert _lib.load().cmbpo_abi_version() == 1
+    assert _lib.load().cmbpo_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from cmbpo_b200 import _lib
     assert ctypes.sizeof(_lib.EnvCfg) == 5 * 4
     assert ctypes.sizeof(_lib.RolloutBufs) == 25 * 8
-    assert _lib.RolloutCfg.env.offset % 4 == 0 and ctypes.sizeof(_lib.RolloutCfg) == 72
+    assert _lib.RolloutCfg.env.offset % 4 == 0 and ctypes.sizeof(_lib.RolloutCfg) == 80
 
 
 def test_no_cpu_fallback():

@@ -236,7 +236,7 @@ def test_standalone_gae_config4(engine):
         assert np.all(np.abs(gw - w) <= np.spacing(np.abs(w)) + 1e-30)
 
 
-def test_alive_row_compaction_is_invisible(engine, monkeypatch):
+def test_alive_row_compaction_is_invisible(engine):
     """Squeezing finished paths out of the batch (tensor-core path, AntSafe + uncertainty cut-off) must
     not change a single bit: a row's result does not depend on which tile / lane it occupies."""
     import cmbpo_b200 as cb
@@ -250,11 +250,10 @@ def test_alive_row_compaction_is_invisible(engine, monkeypatch):
     cfg = L.EnvCfg(L.TERM_ANTSAFE, L.COST_ANTSAFE, 0, 1, 1)
     t = engine.torch
     res = []
-    for no_compact in ("0", "1"):
-        monkeypatch.setenv("CMBPO_NO_COMPACT", no_compact)
+    for flags in (0, L.ROLLOUT_NO_COMPACT):
         bufs = cb.RolloutBuffers(engine, B, T, O, A)
         bufs.set_inputs(obs)
-        bufs.run(cfg, uncertainty_mode=True, dkl_lim=lim, seed=21, precision="fp16")
+        bufs.run(cfg, uncertainty_mode=True, dkl_lim=lim, seed=21, precision="fp16", flags=flags)
         bufs.gae(GAE["gamma"], GAE["lam"], GAE["cost_gamma"], GAE["cost_lam"])
         engine.synchronize()
         res.append(bufs)

@@ -1,6 +1,6 @@
 """Rollout throughput in the reference's default 'uncertainty' mode (paths are cut when their
 cumulative ensemble KL reaches dkl_lim): device-resident rollout + GAE, with and without the
-alive-row compaction (CMBPO_NO_COMPACT=1)."""
+alive-row compaction (flags=L.ROLLOUT_NO_COMPACT)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -21,13 +21,12 @@ base = float(out["dkl_path"].mean())
 bufs = cb.RolloutBuffers(eng, B, T, O, A); bufs.set_inputs(obs)
 for factor in (5.0, 15.0):
     for nc, every in (("0", "1"), ("0", "2"), ("0", "4"), ("1", "4")):
-        os.environ["CMBPO_NO_COMPACT"] = nc
-        os.environ["CMBPO_COMPACT_EVERY"] = every
+        kw = dict(flags=L.ROLLOUT_NO_COMPACT if nc == "1" else 0, compact_every=int(every))
         for i in range(3):
-            bufs.run(cfg, uncertainty_mode=True, dkl_lim=base * factor, seed=i); bufs.gae(0.99, 0.95, 0.97, 0.5)
+            bufs.run(cfg, uncertainty_mode=True, dkl_lim=base * factor, seed=i, **kw); bufs.gae(0.99, 0.95, 0.97, 0.5)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for i in range(6):
-            bufs.run(cfg, uncertainty_mode=True, dkl_lim=base * factor, seed=10 + i); bufs.gae(0.99, 0.95, 0.97, 0.5)
+            bufs.run(cfg, uncertainty_mode=True, dkl_lim=base * factor, seed=10 + i, **kw); bufs.gae(0.99, 0.95, 0.97, 0.5)
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 6
         n = int(bufs.length.sum().item())
         print("dkl_lim = %4.1f x one-step KL, compaction %s: mean path %.1f steps, %.2f ms per rollout, %.1f M transitions/s"
