@@ -54,6 +54,7 @@ struct Net {
     size_t tc_pack_bytes[3] = {0, 0, 0};
     float* tc_bias = nullptr;   // biases re-laid for the epilogue
     int tc_group = 1;           // members per tcgen05 work unit (4 for narrow ensembles)
+    int tc_fold = 0;            // layer-0 bias folded into the packed layer-0 tiles (input dim + 2 <= 64)
     // merged nets only: hidden activation per member (CMBPO_ACT_*); all -1 for an ordinary ensemble
     int member_act[CMBPO_MAX_E] = {-1, -1, -1, -1, -1, -1, -1, -1};
 };

@@ -38,8 +38,9 @@ constexpr int NTHREADS = 640;    // 4 control warps + 16 epilogue warps
 constexpr int TILE = 8192;        // [64 neurons x 64 k x 2 B] weight tile
 constexpr int STAGE = 4 * TILE;   // main-ring stage: up to 4 consecutive tiles (one mbarrier wait per 16 MMAs)
 constexpr int NSM = 5;            // main ring depth (160 KB)
-constexpr int W2SLOT = 24576;     // layer-2 ring slot: the W2 tiles of CPS consecutive chunks
+constexpr int W2SLOT = 16384;     // layer-2 ring slot: the W2 tiles of CPS consecutive chunks (NP <= 128: >= 1 chunk)
 constexpr int NS2 = 2;
+constexpr int BIAS_SLOT = 4096;   // per-unit hidden biases [b0 | b1] (<= 2 x 512 floats), double buffered
 constexpr int XA_BYTES = 16384;   // [128 rows x 64 k x 2 B]
 
 struct Stage {        // one weight tile image in the packed stream
@@ -52,6 +53,7 @@ struct TcParams {
     const uint8_t* w2; unsigned long long w2_bytes;        // per member: layer-2 tiles
     const float* bias; int bias_stride;
     int E, K0, KS0, Nout, NP, parts, cps;        // parts = 2 when NP > 64; cps = chunks per W2 slot
+    int fold;                                    // layer-0 bias rides in the GEMM (XA columns K0, K0+1 = 1)
     const float* x; long long N; int ldx;
     const long long* n_dev;                      // optional: live row count on the device (<= N)
     const float *mu_in, *sig_in;
@@ -65,18 +67,21 @@ struct TcParams {
 // barrier indices
 enum { W_FULL = 0, W_EMPTY = NSM, W2_FULL = 2 * NSM, W2_EMPTY = 2 * NSM + NS2, D_FULL = 2 * NSM + 2 * NS2,
        D_EMPTY = D_FULL + 2, H1_FULL = D_FULL + 4, H2_FULL = D_FULL + 5, H2_EMPTY = D_FULL + 7,
-       OUT_FULL = D_FULL + 9, OUT_EMPTY = D_FULL + 10, X_FULL = D_FULL + 11, NBAR = D_FULL + 12 };
+       OUT_FULL = D_FULL + 9, OUT_EMPTY = D_FULL + 10, X_FULL = D_FULL + 11, B_FULL = D_FULL + 12,
+       B_EMPTY = D_FULL + 14, NBAR = D_FULL + 16 };
 constexpr int SMEM_W2 = XA_BYTES + NSM * STAGE;
-constexpr int SMEM_BAR = SMEM_W2 + NS2 * W2SLOT;
+constexpr int SMEM_BIAS = SMEM_W2 + NS2 * W2SLOT;
+constexpr int SMEM_BAR = SMEM_BIAS + 2 * BIAS_SLOT;
 constexpr int SMEM_TOTAL = SMEM_BAR + NBAR * 8 + 16;
 // FUSE kernels (the rollout step fused around the GEMM chain): the layer-2 ring shrinks to 2 x 12 KB (a
 // 2 x 8 KB ring measured the same as 2 x 24 KB) and the freed shared memory stages the row math:
-//   stage  20 KB   kl, epv per (obs dimension, row) of one pass of RP rows (RP = 128 / 64 / 32 by obs dim)
+//   stage  12 KB   kl, epv per (obs dimension, row) of one pass of RP rows (RP = 64 / 32 by obs dim)
 //   misc    5 KB   per-row member / path / state / non-finite flag, the 4 next-state coordinates the statics
 //                  read, output-scaler vectors, log_std, elite list, the "last arriver" flag
 constexpr int W2SLOT_F = 12288;
-constexpr int FZ_STAGE = 20480, FZ_MISC = 5120;
-constexpr int SMEM_BAR_F = SMEM_W2 + NS2 * W2SLOT_F;
+constexpr int FZ_STAGE = 12288, FZ_MISC = 5120;
+constexpr int SMEM_BIAS_F = SMEM_W2 + NS2 * W2SLOT_F;
+constexpr int SMEM_BAR_F = SMEM_BIAS_F + 2 * BIAS_SLOT;
 constexpr int SMEM_FZ = SMEM_BAR_F + NBAR * 8 + 16;
 constexpr int SMEM_TOTAL_F = SMEM_FZ + FZ_STAGE + FZ_MISC;
 static_assert(SMEM_FZ % 16 == 0 && SMEM_TOTAL_F + 1024 <= 232448, "fused shared-memory budget");
@@ -228,12 +233,16 @@ __device__ __forceinline__ void fused_rows(const FusedStep& f, const FzSmem& sm,
 
 
 // event trace of CTA 0, member 8 (steady state), kept in shared memory so that tracing does not
-// perturb the timeline; 3 streams (MMA warp, epilogue pair 0, pair 1) x 64 events of (tag, clock)
+// perturb the timeline; 5 streams (MMA thread, the lane-quarter-0 warp of each epilogue warpgroup) x 40
+// events of (tag, clock)
+#define TRACE_EVENTS 48
+#define TRACE_WORDS (2 + 2 * TRACE_EVENTS)
+#define TRACE_STREAMS 5
 #define TRACE(stream, tag)                                                                    \
-    if (DBG && p.dbg && blockIdx.x == 0 && m == 8 && lane == 0 && (warp & 3) == ((stream) == 0 ? 1 : 0)) { \
-        uint32_t* t_ = trace_smem + (stream) * 130;                                           \
+    if (DBG && p.dbg && blockIdx.x == 0 && m == 8 && lane == 0 && (warp == 1 || (warp & 3) == 0)) { \
+        uint32_t* t_ = trace_smem + (stream) * TRACE_WORDS;                                   \
         uint32_t n_ = t_[0];                                                                  \
-        if (n_ < 64) { t_[2 + n_ * 2] = (tag); t_[3 + n_ * 2] = (uint32_t)clock64(); t_[0] = n_ + 1; } \
+        if (n_ < TRACE_EVENTS) { t_[2 + n_ * 2] = (tag); t_[3 + n_ * 2] = (uint32_t)clock64(); t_[0] = n_ + 1; } \
     }
 
 // debug builds only: 1 = also accumulate the cycles spent in every wait (perturbs the timeline),
@@ -251,18 +260,18 @@ __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, unsigned 
     }
 }
 
-template <int ACT> __device__ __forceinline__ float activate(float x) {
-    if (ACT == CMBPO_ACT_SWISH) return swish_fast(x);
-    if (ACT == CMBPO_ACT_TANH) return tanh_approx(x);
-    return x;
-}
-
-// 32 accumulator columns of this thread's row -> +bias, act -> 16-bit pairs -> 16 TMEM columns.
+// 32 accumulator columns of this thread's row -> (+bias), act -> 16-bit pairs -> 16 TMEM columns.
 // The accumulator buffer is released (`d_empty`) as soon as the values sit in registers; the
-// destination is only waited for (`dst_free`, may be null) right before the store.
+// destination is only waited for (`dst_free`, 0 = none) right before the store.
+//
+// Swish members are packed with their hidden-layer weights and biases HALVED (exact in 16 bits), so the
+// accumulator already holds t = x/2 and swish(x) = t + t tanh t needs one MUFU and one FFMA.  `bias`
+// points at this warp's 32 biases in shared memory (every lane reads the same address: a broadcast
+// LDS.128 per four elements; the earlier per-element SHFL of a lane-held bias shared the MIO queue with
+// the MUFU instructions) or is null when the bias rides in the GEMM (layer 0, see `fold`).
 template <int FMT, int ACT>
-__device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32_t dst_addr,
-                                        uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity,
+__device__ __forceinline__ void drain32(uint32_t d_addr, const float* bias, uint32_t dst_addr,
+                                        uint32_t d_empty, uint32_t dst_free, uint32_t dst_parity,
                                         uint32_t* tr = nullptr) {
     uint32_t r[32];
     tmem_ld32(d_addr, r);
@@ -270,31 +279,26 @@ __device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32
     if (tr) tr[0] = (uint32_t)clock64();
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(d_empty);
+    if ((threadIdx.x & 31) == 0) mbar_arrive_a(d_empty);
     uint32_t q[16];
-    // lane l holds bias[l] of this warp's 32 columns (one coalesced load issued BEFORE the accumulator
-    // wait; shared memory is carved to the limit so there is no L1 to serve per-thread bias loads).
-    // The 32 elements are independent: straight-line code (no branch inside the loops) lets the
-    // scheduler overlap the shuffle / MUFU latencies of all of them.
     float v[32];
-    if (ACT == CMBPO_ACT_SWISH) {
-        // swish(x) = t + t tanh t with t = x/2 = fma(acc, 0.5, bias/2): 4.5 instructions per element
-        // (SHFL, FFMA, MUFU, FFMA, half a packed saturating convert)
-        const float hb = 0.5f * bias_lane;
+    if (bias) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), 0.5f, __shfl_sync(0xffffffffu, hb, i));
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = swish_half(v[i]);
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + i);
+            v[i] = __uint_as_float(r[i]) + b.x; v[i + 1] = __uint_as_float(r[i + 1]) + b.y;
+            v[i + 2] = __uint_as_float(r[i + 2]) + b.z; v[i + 3] = __uint_as_float(r[i + 3]) + b.w;
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + __shfl_sync(0xffffffffu, bias_lane, i);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = activate<ACT>(v[i]);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
     }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (ACT == CMBPO_ACT_SWISH) ? swish_half(v[i]) : tanh_approx(v[i]);
 #pragma unroll
     for (int c = 0; c < 16; ++c) q[c] = Cvt<FMT>::pack(v[2 * c], v[2 * c + 1]);
     if (tr) tr[1] = (uint32_t)clock64();
-    if (dst_free) { mbar_wait(dst_free, dst_parity); tc_fence_after(); }
+    if (dst_free) { mbar_wait_a(dst_free, dst_parity); tc_fence_after(); }
     tmem_st16(dst_addr, q);
     tmem_st_wait();
     tc_fence_before();
@@ -303,15 +307,15 @@ __device__ __forceinline__ void drain32(uint32_t d_addr, float bias_lane, uint32
 
 // ACT == 0: the activation is a per-member runtime value (merged policy ensemble)
 template <int FMT, int ACT>
-__device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, float bias_lane, uint32_t dst_addr,
-                                            uint64_t* d_empty, uint64_t* dst_free, uint32_t dst_parity,
+__device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, const float* bias, uint32_t dst_addr,
+                                            uint32_t d_empty, uint32_t dst_free, uint32_t dst_parity,
                                             uint32_t* tr = nullptr) {
     if (ACT != 0) {
-        drain32<FMT, ACT>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity, tr);
+        drain32<FMT, ACT>(d_addr, bias, dst_addr, d_empty, dst_free, dst_parity, tr);
     } else if (act_rt == CMBPO_ACT_TANH) {
-        drain32<FMT, CMBPO_ACT_TANH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity);
+        drain32<FMT, CMBPO_ACT_TANH>(d_addr, bias, dst_addr, d_empty, dst_free, dst_parity);
     } else {
-        drain32<FMT, CMBPO_ACT_SWISH>(d_addr, bias_lane, dst_addr, d_empty, dst_free, dst_parity);
+        drain32<FMT, CMBPO_ACT_SWISH>(d_addr, bias, dst_addr, d_empty, dst_free, dst_parity);
     }
 }
 
@@ -335,11 +339,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     uint8_t* sXA = smem;
     uint8_t* sW = smem + XA_BYTES;
     uint8_t* sW2 = smem + SMEM_W2;
+    float* sBias = reinterpret_cast<float*>(smem + (FUSE ? SMEM_BIAS_F : SMEM_BIAS));
     constexpr int BAR_OFF = FUSE ? SMEM_BAR_F : SMEM_BAR;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NBAR * 8);
-    uint32_t* trace_smem = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NBAR * 8 + 16);   // DBG only (1560 B)
-    if (DBG && threadIdx.x < 3) trace_smem[threadIdx.x * 130] = 0;
+    uint32_t* trace_smem = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NBAR * 8 + 16);   // DBG only (1960 B)
+    if (DBG && threadIdx.x < TRACE_STREAMS) trace_smem[threadIdx.x * TRACE_WORDS] = 0;
 
     // Warp roles: 0 = main weight producer, 1 = layer-0/1 MMA issuer, 2 = TMEM allocator + layer-2 MMA
     // issuer, 3 = W2 producer, 4-19 = epilogue (four warpgroups).  A warp may only touch the TMEM lane
@@ -360,6 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         mbar_init(bar + H1_FULL, 8 * NC);
         mbar_init(bar + OUT_FULL, 1); mbar_init(bar + OUT_EMPTY, 16);
         mbar_init(bar + X_FULL, 4);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar + B_FULL + i, 1); mbar_init(bar + B_EMPTY + i, 16); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -421,11 +427,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         }
     } else if (warp == 3) {
         // ===== layer-2 weight producer: the W2 tiles of `cps` consecutive chunks per slot =====
-        uint32_t s2 = 0, ph2 = 0;
+        uint32_t s2 = 0, ph2 = 0, mb = 0;
         unsigned long long dummy = 0;
-        for (long long u = u0; u < u1; ++u) {
+        for (long long u = u0; u < u1; ++u, ++mb) {
             {
                 const int e = (int)(u % n_groups);
+                {   // hidden-layer biases [b0 | b1] of this unit -> bias buffer (mb & 1)
+                    wait_t<false>(bar + B_EMPTY + (mb & 1), ((mb >> 1) & 1) ^ 1, dummy);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar + B_FULL + (mb & 1), 2 * HD * 4);
+                        bulk_g2s(sBias + (mb & 1) * (BIAS_SLOT / 4), p.bias + (long long)e * p.bias_stride, 2 * HD * 4,
+                                 bar + B_FULL + (mb & 1));
+                    }
+                    __syncwarp();
+                }
                 const uint8_t* src = p.w2 + (unsigned long long)e * p.w2_bytes;
                 for (int j0 = 0; j0 < NC; j0 += p.cps) {
                     const int nchunks = (NC - j0) < p.cps ? (NC - j0) : p.cps;
@@ -488,8 +503,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         // included, so that no warp-level election / reconvergence sits between two batches of MMAs
         // (-6% on the 512-wide ensemble).  Grouped narrow members have short batches and are paced by
         // the drains; there the warp-uniform loop with a per-batch election measured 5% faster. =====
+        #ifdef CMBPO_NO_SINGLE
+        constexpr bool SINGLE = false;
+#else
         constexpr bool SINGLE = (G == 1);
+#endif
         const uint32_t idesc_h = idesc_f16(FMT, 64), idesc_h2 = idesc_f16(FMT, 128);
+        // the tensor-memory base as a RUN-TIME value (it is 0, checked above): with a compile-time base ptxas
+        // folds the chained operand addresses of mma_f16_ts_tiles back into one constant + R2UR per MMA
+        const uint32_t tmem_rt = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         const uint64_t dXA = smem_desc_sw128(smem_u32(sXA));
         const uint64_t dW0 = smem_desc_sw128(smem_u32(sW));
         uint32_t s = 0, ph = 0, g = 0, m = 0, it = 0;
@@ -509,6 +531,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             {
                 for (int j0 = 0; j0 < NC; j0 += G0) {       // layer 0: D = XA x W0 chunk (G0 chunks per stage)
                     wait_t<DBG>(bar + W_FULL + s, ph, c_w);
+#ifdef CMBPO_L0_SPLIT
+#pragma unroll
+                    for (int jj = 0; jj < G0; ++jj) {
+                        // one chunk per instruction, buffer = chunk parity: the two epilogue pairs run as
+                        // independent streams (one computes while the other is in its hand-off)
+                        const uint32_t buf = g & 1, n = g >> 1;
+                        wait_t<DBG>(bar + D_EMPTY + buf, (n & 1) ^ 1, c_d);
+                        tc_fence_after();
+                        if (SINGLE || elect_one()) {
+                            const uint64_t dB = dW0 + (uint64_t)((s * STAGE + jj * TILE) >> 4);
+                            for (int ks = 0; ks < p.KS0; ++ks)
+                                mma_f16(tmem + COL_D + buf * 64, dXA + 2 * ks, dB + 2 * ks, idesc_h, ks > 0);
+                            mma_commit(bar + D_FULL + buf);
+                            if (jj == G0 - 1) mma_commit(bar + W_EMPTY + s);
+                        }
+                        if (!SINGLE) __syncwarp();
+                        TRACE(0, 100 + j0 + jj);
+                        g += 1;
+                    }
+#else
 #pragma unroll
                     for (int jj = 0; jj < G0; jj += 2) {
                         // two chunks per instruction (N = 128 fills both accumulator buffers; their
@@ -530,6 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                         TRACE(0, 100 + j0 + jj);
                         g += 2;
                     }
+#endif
                     next_stage();
                 }
                 wait_t<DBG>(bar + H1_FULL, m & 1, c_h1);
@@ -543,15 +586,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     for (int kq = 0; kq < KP / TPS; ++kq) {
                         wait_t<DBG>(bar + W_FULL + s, ph, c_w);      // TMA completion: no tcgen05 fence needed
                         if (SINGLE || elect_one()) {
-#pragma unroll
-                            for (int tt = 0; tt < TPS; ++tt) {
-                                const uint64_t dB = dW0 + (uint64_t)((s * STAGE + tt * TILE) >> 4);
-                                const uint32_t aT = tmem + COL_H1 + ((j / CPM) * KP + kq * TPS + tt) * 32;
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    mma_f16_ts(tmem + COL_D + buf * 64, aT + ks * 8, dB + 2 * ks, idesc_h,
-                                               (kq | tt | ks) > 0);
-                            }
+                            // TPS tiles x 4 K-steps from one asm statement (addresses chained inside, see tc_common.cuh)
+                            mma_f16_ts_tiles<TPS>(tmem + COL_D + buf * 64, tmem_rt + COL_H1 + ((j / CPM) * KP + kq * TPS) * 32,
+                                                  dW0 + (uint64_t)((s * STAGE) >> 4), idesc_h, kq > 0);
                             mma_commit(bar + W_EMPTY + s);
                             if (kq == KP / TPS - 1) mma_commit(bar + D_FULL + buf);
                         }
@@ -580,6 +617,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         const int wq = hw_warp & 3;                // TMEM lane quarter this warp may access
         const int row = wq * 32 + lane;
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        const uint32_t bar_a = smem_u32(bar);
         uint32_t g = 0, m = 0, c1 = 0;
         unsigned long long c_dfull = 0, c_drain = 0, c_outw = 0;
         uint32_t dtr[3] = {0, 0, 0};
@@ -710,7 +748,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int k = c * 8 + i;
-                        float t = 0.f;
+                        float t = (p.fold && feed && (k == p.K0 || k == p.K0 + 1)) ? 1.0f : 0.f;
                         if (k < p.K0 && feed) {
                             if (FUSE) t = (k < p.fz.O) ? p.fz.cur_obs[grow * p.fz.O + k] : p.fz.pi[grow * p.fz.A + (k - p.fz.O)];
                             else t = xr[k];
@@ -731,34 +769,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             }
             {
                 const int e = (int)(u % n_groups);
-                const float* bias = p.bias + (long long)e * p.bias_stride;
                 // Each pair drains every other chunk (chunk j <-> accumulator buffer j&1 <-> pair), so the
-                // loops below run over this pair's chunks only.  The bias of the NEXT drain (lane l holds
-                // bias[l] of this warp's 32 columns) is loaded one drain ahead: its latency hides behind
-                // the current drain / the accumulator wait, and the loops stay rolled (the fully unrolled
-                // variant overflowed the instruction cache and doubled the drain time).
-                float bias_next = __ldg(bias + pair * 64 + half * 32 + lane);
+                // loops below run over this pair's chunks only; they stay rolled (the fully unrolled variant
+                // overflowed the instruction cache and doubled the drain time).  The unit's hidden biases
+                // were copied to shared memory by the layer-2 producer warp.
+                const float* sb = sBias + (m & 1) * (BIAS_SLOT / 4);
+                mbar_wait_a(bar_a + 8 * (B_FULL + (m & 1)), (m >> 1) & 1);
                 for (int i = 0; i < NC / 2; ++i) {               // layer-0 chunk j -> H1 columns
                     const int j = 2 * i + (int)pair;
                     const uint32_t gg = g + j, buf = pair, n = gg >> 1;
-                    const float bias_lane = bias_next;
-                    bias_next = (i + 1 < NC / 2) ? __ldg(bias + (j + 2) * 64 + half * 32 + lane)
-                                                 : __ldg(bias + HD + pair * 64 + half * 32 + lane);
                     wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
                     tc_fence_after();
-                    if (half == 0) { TRACE(1 + pair, 1000 + j); }
+                    TRACE(1 + wg, 1000 + j);
                     const long long td = (DBG && g_tc_count_waits) ? clock64() : 0;
-                    drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
-                                      tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar + D_EMPTY + buf, nullptr, 0,
-                                      (DBG && g_tc_count_waits) ? dtr : nullptr);
-                    if (DBG && half == 0 && pair == 0 && m == 8 && lane == 0 && (warp & 3) == 0 && p.dbg && blockIdx.x == 0) {
-                        uint32_t* t_ = trace_smem + 130; uint32_t n_ = t_[0];
-                        if (n_ + 3 <= 64) { for (int q_ = 0; q_ < 3; ++q_) { t_[2 + (n_ + q_) * 2] = 1200 + q_; t_[3 + (n_ + q_) * 2] = dtr[q_]; } t_[0] = n_ + 3; }
+                    drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base,
+                                      p.fold ? nullptr : sb + j * 64 + half * 32,
+                                      tmem + COL_H1 + j * 32 + half * 16 + lane_base, bar_a + 8 * (D_EMPTY + buf), 0u, 0u,
+                                      DBG ? dtr : nullptr);
+                    if (DBG && m == 8 && lane == 0 && (warp & 3) == 0 && p.dbg && blockIdx.x == 0) {
+                        uint32_t* t_ = trace_smem + (1 + wg) * TRACE_WORDS; uint32_t n_ = t_[0];
+                        if (n_ + 3 <= TRACE_EVENTS) { for (int q_ = 0; q_ < 3; ++q_) { t_[2 + (n_ + q_) * 2] = 1200 + q_; t_[3 + (n_ + q_) * 2] = dtr[q_]; } t_[0] = n_ + 3; }
                     }
                     if (DBG && g_tc_count_waits) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar + H1_FULL);
-                    if (half == 0) { TRACE(1 + pair, 1100 + j); }
+                    if (lane == 0) mbar_arrive_a(bar_a + 8 * H1_FULL);
+                    TRACE(1 + wg, 1100 + j);
                 }
                 g += NC;
                 // The previous member's OUT accumulator is drained HERE, after this member's layer-0
@@ -775,22 +810,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     // the parity test of the phase before (seen as an intermittent dead-lock with 256-wide
                     // nets and two-part outputs).
                     const uint32_t hbar = cc & 1, hn = cc >> 1, hb = (nh2 == 2) ? hbar : 0;
-                    uint64_t* h2_free = (nh2 == 2) ? bar + H2_EMPTY + hbar : (cc == 0 ? nullptr : bar + H2_EMPTY + (hbar ^ 1));
+                    const uint32_t h2_free = (nh2 == 2) ? bar_a + 8 * (H2_EMPTY + hbar) : (cc == 0 ? 0u : bar_a + 8 * (H2_EMPTY + (hbar ^ 1)));
                     const uint32_t h2_par = (nh2 == 2) ? ((hn & 1) ^ 1) : ((((cc - 1) >> 1)) & 1);
-                    const float bias_lane = bias_next;
-                    if (i + 1 < NC / 2) bias_next = __ldg(bias + HD + (j + 2) * 64 + half * 32 + lane);
                     wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
                     tc_fence_after();
-                    if (half == 0) { TRACE(1 + pair, 2000 + j); }
+                    TRACE(1 + wg, 2000 + j);
                     const long long td = (DBG && g_tc_count_waits) ? clock64() : 0;
-                    drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, bias_lane,
-                                      tmem + COL_H2 + hb * 32 + half * 16 + lane_base, bar + D_EMPTY + buf,
-                                      h2_free, h2_par);
+                    drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base,
+                                      sb + HD + j * 64 + half * 32,
+                                      tmem + COL_H2 + hb * 32 + half * 16 + lane_base, bar_a + 8 * (D_EMPTY + buf),
+                                      h2_free, h2_par, DBG ? dtr : nullptr);
+                    if (DBG && m == 8 && lane == 0 && (warp & 3) == 0 && p.dbg && blockIdx.x == 0) {
+                        uint32_t* t_ = trace_smem + (1 + wg) * TRACE_WORDS; uint32_t n_ = t_[0];
+                        if (n_ + 3 <= TRACE_EVENTS) { for (int q_ = 0; q_ < 3; ++q_) { t_[2 + (n_ + q_) * 2] = 2200 + q_; t_[3 + (n_ + q_) * 2] = dtr[q_]; } t_[0] = n_ + 3; }
+                    }
                     if (DBG && g_tc_count_waits) c_drain += (unsigned long long)(clock64() - td);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar + H2_FULL + hbar);
-                    if (half == 0) { TRACE(1 + pair, 2100 + j); }
+                    if (lane == 0) mbar_arrive_a(bar_a + 8 * (H2_FULL + hbar));
+                    TRACE(1 + wg, 2100 + j);
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(bar_a + 8 * (B_EMPTY + (m & 1)));     // the bias buffer may be refilled
                 g += NC; c1 += NC;
                 prev_e = e; prev_grow = grow; prev_m = m; prev_tile = tile; have_prev = true;
                 ++m;
@@ -806,17 +846,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     tc_fence_before();
     __syncthreads();
     if (DBG && p.dbg && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < 390; i += NTHREADS) p.dbg[4096 + i] = trace_smem[i];
+        for (int i = threadIdx.x; i < TRACE_STREAMS * TRACE_WORDS; i += NTHREADS) p.dbg[4096 + i] = trace_smem[i];
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
 // ---- weight packing -----------------------------------------------------------------------------
 // W_l fp32 [E, K, M] (k-major rows, fc.py layout) -> stream of swizzled B tiles: tile row n = output
 // neuron n0+n, 64 consecutive k from k0; zero padded.
+//
+// Two things are folded into the packed hidden layers (both exact in the 16-bit formats):
+//  * swish members: W0, W1 (and the hidden biases) are HALVED, so the accumulators hold t = x/2 and the
+//    epilogue evaluates swish(x) = t + t tanh t without the multiply;
+//  * `fold`: the layer-0 bias rides in the GEMM -- rows K0 and K0+1 of the layer-0 tile hold the bias as a
+//    (hi, lo) pair of 16-bit values (together ~21 mantissa bits) and the input panel holds 1.0 in those two
+//    columns, which removes the bias add from the drain-bound layer-0 epilogue.  Needs K0 + 2 <= 64.
+struct PackCfg { int fold; int act[CMBPO_MAX_E]; };
+
+template <int FMT> __device__ __forceinline__ uint16_t to16(float v) {
+    if (FMT == 0) { __half x = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); return *reinterpret_cast<uint16_t*>(&x); }
+    __nv_bfloat16 x = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&x);
+}
+template <int FMT> __device__ __forceinline__ float from16(uint16_t h) {
+    if (FMT == 0) return __half2float(*reinterpret_cast<__half*>(&h));
+    return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&h));
+}
+
 template <int FMT>
-__global__ void pack_weights_kernel(const float* W0, const float* W1, const float* W2, int K0, int HD,
+__global__ void pack_weights_kernel(const float* W0, const float* W1, const float* W2, const float* b0, int K0, int HD,
                                     int Nout, int E, int group, const Stage* stages, int n_stages,
-                                    unsigned long long member_bytes, uint8_t* out) {
+                                    unsigned long long member_bytes, PackCfg cfg, uint8_t* out) {
     const Stage st = stages[blockIdx.x];
     const int e = blockIdx.y * group + st.member;        // real member (may be >= E in the last group: zeros)
     const float* W; int K, M;
@@ -824,31 +882,36 @@ __global__ void pack_weights_kernel(const float* W0, const float* W1, const floa
     else if (st.layer == 1) { W = W1 + (size_t)e * HD * HD; K = HD; M = HD; }
     else { W = W2 + (size_t)e * HD * Nout; K = HD; M = Nout; }
     if (e >= E) K = 0;
+    const float scale = (st.layer < 2 && e < E && cfg.act[e] == CMBPO_ACT_SWISH) ? 0.5f : 1.0f;
     uint8_t* dst = out + (size_t)blockIdx.y * member_bytes + st.off;
     for (int idx = threadIdx.x; idx < st.rows * 64; idx += blockDim.x) {
         const int n = idx >> 6, k = idx & 63;
         const int gk = st.k0 + k, gn = st.n0 + n;
-        float v = (gk < K && gn < M) ? W[(size_t)gk * M + gn] : 0.f;
-        uint16_t h;
-        if (FMT == 0) { __half x = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); h = *reinterpret_cast<uint16_t*>(&x); }
-        else { __nv_bfloat16 x = __float2bfloat16_rn(v); h = *reinterpret_cast<uint16_t*>(&x); }
+        float v = (gk < K && gn < M) ? scale * W[(size_t)gk * M + gn] : 0.f;
+        uint16_t h = to16<FMT>(v);
+        if (st.layer == 0 && cfg.fold && e < E && gn < M && (gk == K0 || gk == K0 + 1)) {
+            const float b = scale * b0[(size_t)e * HD + gn];
+            const uint16_t hi = to16<FMT>(b);
+            h = (gk == K0) ? hi : to16<FMT>(b - from16<FMT>(hi));
+        }
         *reinterpret_cast<uint16_t*>(dst + panel_off(n, k >> 3) + (k & 7) * 2) = h;
     }
 }
 
-// per unit: [b0 of the G members | b1 of the G members | b2 (NP each) of the G members]; HD = member width
+// per unit: [b0 of the G members | b1 of the G members | b2 (NP each) of the G members]; HD = member width.
+// The hidden biases of swish members are halved like their weights.
 __global__ void pack_bias_kernel(const float* b0, const float* b1, const float* b2, int HD, int Nout, int NP,
-                                 int E, int group, float* out) {
+                                 int E, int group, PackCfg cfg, float* out) {
     const int u = blockIdx.x;
     const int stride = group * (2 * HD + NP);
     for (int i = threadIdx.x; i < stride; i += blockDim.x) {
         float v = 0.f;
         if (i < group * HD) {
             const int e = u * group + i / HD;
-            if (e < E) v = b0[(size_t)e * HD + i % HD];
+            if (e < E) v = b0[(size_t)e * HD + i % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
         } else if (i < 2 * group * HD) {
             const int k = i - group * HD, e = u * group + k / HD;
-            if (e < E) v = b1[(size_t)e * HD + k % HD];
+            if (e < E) v = b1[(size_t)e * HD + k % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
         } else {
             const int k = i - 2 * group * HD, e = u * group + k / NP, c = k % NP;
             if (e < E && c < Nout) v = b2[(size_t)e * Nout + c];
@@ -897,8 +960,8 @@ int chunks_per_w2_slot(int HD, int NP, int slot_bytes = W2SLOT) {
 
 template <int HD, int FMT, int ACT, bool DBG, int G = 1, bool FUSE = false>
 int launch_tc(cmbpo_ctx* ctx, const TcParams& p) {
-    const int smem = (FUSE ? SMEM_TOTAL_F : SMEM_TOTAL) + 1024 + (DBG ? 1568 : 0);
-    static_assert(SMEM_TOTAL + 1024 + 1568 <= 232448, "shared memory budget");
+    const int smem = (FUSE ? SMEM_TOTAL_F : SMEM_TOTAL) + 1024 + (DBG ? 1968 : 0);
+    static_assert(SMEM_TOTAL + 1024 + 1968 <= 232448, "shared memory budget");
     auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT, DBG, G, FUSE>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const long long units = (long long)p.ntiles * ((p.E + G - 1) / G);
@@ -961,6 +1024,10 @@ int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
     unsigned long long main_bytes = 0, w2_bytes = 0;
     std::vector<Stage> mp, wp;
     stage_programs(HD * group, os.NP, os.parts, group, &mp, &main_bytes, &wp, &w2_bytes);
+    PackCfg pc;
+    pc.fold = (K0 + 2 <= 64) ? 1 : 0;
+    for (int e = 0; e < CMBPO_MAX_E; ++e) pc.act[e] = net.member_act[0] >= 0 ? net.member_act[e] : net.acts[0];
+    net.tc_fold = pc.fold;
     Stage *d_mp, *d_wp;
     CUDA_TRY(cudaMalloc(&d_mp, mp.size() * sizeof(Stage)));
     CUDA_TRY(cudaMalloc(&d_wp, wp.size() * sizeof(Stage)));
@@ -974,15 +1041,15 @@ int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
         uint8_t* base2 = base + (size_t)n_units * main_bytes;
         dim3 g1((unsigned)mp.size(), n_units), g2((unsigned)wp.size(), n_units);
         if (prec == CMBPO_PREC_FP16) {
-            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, base);
-            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, base2);
+            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HD, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
+            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HD, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
         } else {
-            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, base);
-            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], K0, HD, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, base2);
+            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HD, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
+            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HD, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
         }
     }
     CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)n_units * group * (2 * HD + os.NP) * sizeof(float)));
-    pack_bias_kernel<<<n_units, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, Nout, os.NP, net.E, group, net.tc_bias);
+    pack_bias_kernel<<<n_units, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, Nout, os.NP, net.E, group, pc, net.tc_bias);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaFree(d_mp));
     CUDA_TRY(cudaFree(d_wp));
@@ -1025,7 +1092,7 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     p.w2_bytes = (unsigned long long)(HD * net.tc_group / 64) * p.NP * 128;
     const int group = net.tc_group, n_units = (net.E + group - 1) / group;
     p.bias = net.tc_bias; p.bias_stride = group * (2 * HD + p.NP);
-    p.E = net.E; p.K0 = net.dims[0]; p.KS0 = (p.K0 + 15) / 16;
+    p.E = net.E; p.K0 = net.dims[0]; p.fold = net.tc_fold; p.KS0 = (p.K0 + (p.fold ? 2 : 0) + 15) / 16;
     p.x = x; p.N = N; p.ldx = net.dims[0];
     p.n_dev = reinterpret_cast<const long long*>(n_dev);
     p.mu_in = net.has_in ? net.mu_in : nullptr; p.sig_in = net.sig_in;
@@ -1072,11 +1139,12 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
         }
         static int printed = 0;
         if (!printed++) {
-            for (int st = 0; st < 3; ++st) {
-                const unsigned long long* t = h.data() + 4096 + st * 130;
+            static const char* names_s[TRACE_STREAMS] = {"mma", "epi wg0", "epi wg1", "epi wg2", "epi wg3"};
+            for (int st = 0; st < TRACE_STREAMS; ++st) {
+                const unsigned long long* t = h.data() + 4096 + st * TRACE_WORDS;
                 uint32_t t0 = (uint32_t)h[4096 + 3];     // first MMA event
-                fprintf(stderr, "trace stream %d (%s):", st, st == 0 ? "mma" : (st == 1 ? "epi pair0" : "epi pair1"));
-                for (unsigned long long i = 0; i < t[0] && i < 64; ++i)
+                fprintf(stderr, "trace stream %d (%s):", st, names_s[st]);
+                for (unsigned long long i = 0; i < t[0] && i < TRACE_EVENTS; ++i)
                     fprintf(stderr, " %llu@%d", t[2 + i * 2], (int)((uint32_t)t[3 + i * 2] - t0));
                 fprintf(stderr, "\n");
             }

@@ -44,6 +44,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
+// Suspend-time hint of every try_wait (ns): without it a try_wait on an incomplete phase returns after a
+// few tens of cycles, and the spin loops of the ~10 waiting warps of a CTA issue as many instructions as
+// the warps doing the epilogue arithmetic -- on the same issue ports and the same MIO queues as their
+// MUFU / LDS instructions (ncu: 25 M try_wait executions per launch against 0.7 M useful waits).
+#ifndef MBAR_SUSPEND_NS
+#define MBAR_SUSPEND_NS 20000u
+#endif
 // Bounded spin: a protocol bug must not hang the GPU (a hung box is a lost box).  On timeout the
 // kernel traps, which surfaces as a launch failure on the host.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -53,19 +60,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
     // a try_wait suspends for up to ~9 us (measured: 2^26 spins = 9.6 min): 2^19 spins trap a deadlock
     // after ~4.5 s, three orders of magnitude above any legitimate wait
-    for (uint32_t spin = 0; spin < (1u << 19); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(MBAR_SUSPEND_NS)
             : "memory");
         if (done) return;
     }
     // No printf here: a device-side call in each of the ~20 inlined wait sites costs the kernel 10 %
     // (caller-saved registers around the call constrain the allocation of the hot loops).  The trap
     // surfaces as a launch failure on the host; CMBPO_TC_DEBUG builds narrow it down.
+    __trap();
+}
+
+// the same on a precomputed shared-window address (the generic -> shared conversion of a pointer costs
+// two special-register reads per use in the hot loops)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(MBAR_SUSPEND_NS)
+            : "memory");
+        if (done) return;
+    }
     __trap();
 }
 
@@ -215,5 +243,47 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+}  // namespace tc
+
+namespace tc {
+// NT consecutive B tiles ([64 x 64] 16-bit, 8 KB apart) x 4 K-steps of TS-form MMAs into ONE accumulator, issued
+// from a single asm statement whose operand addresses are derived by add instructions from the two bases.
+// With one C++-level operand per MMA, ptxas materialises every tensor-memory address and descriptor in a
+// general register and moves it to a uniform register (IMAD.MOV + R2UR per operand: ~40 per 16 MMAs), which
+// made the issuing thread -- not the tensor pipe -- the bound of the layer-1 phase.  Chained adds stay on the
+// uniform datapath after one R2UR per base.
+#define CMBPO_MMA_TS_STEP(P)                                                             \
+    "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, " P ";\n\t"                  \
+    "add.u32 ta, ta, 8;\n\tadd.u64 db, db, 2;\n\t"
+#define CMBPO_MMA_TS_TILE(P0)                                                            \
+    CMBPO_MMA_TS_STEP(P0) CMBPO_MMA_TS_STEP("pt") CMBPO_MMA_TS_STEP("pt") CMBPO_MMA_TS_STEP("pt") \
+    "add.u64 db, db, 504;\n\t"
+template <int NT>
+__device__ __forceinline__ void mma_f16_ts_tiles(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate_first) {
+    static_assert(NT == 1 || NT == 2 || NT == 4, "tiles per stage");
+    if (NT == 4) {
+        asm volatile(
+            "{\n\t.reg .pred p0, pt;\n\t.reg .b32 ta;\n\t.reg .b64 db;\n\t"
+            "setp.ne.b32 p0, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tmov.b32 ta, %1;\n\tmov.b64 db, %2;\n\t"
+            CMBPO_MMA_TS_TILE("p0") CMBPO_MMA_TS_TILE("pt") CMBPO_MMA_TS_TILE("pt") CMBPO_MMA_TS_TILE("pt")
+            "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate_first)
+            : "memory");
+    } else if (NT == 2) {
+        asm volatile(
+            "{\n\t.reg .pred p0, pt;\n\t.reg .b32 ta;\n\t.reg .b64 db;\n\t"
+            "setp.ne.b32 p0, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tmov.b32 ta, %1;\n\tmov.b64 db, %2;\n\t"
+            CMBPO_MMA_TS_TILE("p0") CMBPO_MMA_TS_TILE("pt")
+            "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate_first)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p0, pt;\n\t.reg .b32 ta;\n\t.reg .b64 db;\n\t"
+            "setp.ne.b32 p0, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tmov.b32 ta, %1;\n\tmov.b64 db, %2;\n\t"
+            CMBPO_MMA_TS_TILE("p0")
+            "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate_first)
+            : "memory");
+    }
 }
 }  // namespace tc
