@@ -71,7 +71,8 @@ enum { W_FULL = 0, W_EMPTY = NSM, W2_FULL = 2 * NSM, W2_EMPTY = 2 * NSM + NS2, D
        B_EMPTY = D_FULL + 14, NBAR = D_FULL + 16 };
 constexpr int SMEM_W2 = XA_BYTES + NSM * STAGE;
 constexpr int SMEM_BIAS = SMEM_W2 + NS2 * W2SLOT;
-constexpr int SMEM_BAR = SMEM_BIAS + 2 * BIAS_SLOT;
+constexpr int SMEM_IN_BYTES = 512;   // input scaler: mu[64] | sigma[64]
+constexpr int SMEM_BAR = SMEM_BIAS + 2 * BIAS_SLOT + SMEM_IN_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + NBAR * 8 + 16;
 // FUSE kernels (the rollout step fused around the GEMM chain): the layer-2 ring shrinks to 2 x 12 KB (a
 // 2 x 8 KB ring measured the same as 2 x 24 KB) and the freed shared memory stages the row math:
@@ -81,7 +82,7 @@ constexpr int SMEM_TOTAL = SMEM_BAR + NBAR * 8 + 16;
 constexpr int W2SLOT_F = 12288;
 constexpr int FZ_STAGE = 12288, FZ_MISC = 5120;
 constexpr int SMEM_BIAS_F = SMEM_W2 + NS2 * W2SLOT_F;
-constexpr int SMEM_BAR_F = SMEM_BIAS_F + 2 * BIAS_SLOT;
+constexpr int SMEM_BAR_F = SMEM_BIAS_F + 2 * BIAS_SLOT + SMEM_IN_BYTES;
 constexpr int SMEM_FZ = SMEM_BAR_F + NBAR * 8 + 16;
 constexpr int SMEM_TOTAL_F = SMEM_FZ + FZ_STAGE + FZ_MISC;
 static_assert(SMEM_FZ % 16 == 0 && SMEM_TOTAL_F + 1024 <= 232448, "fused shared-memory budget");
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     uint8_t* sW = smem + XA_BYTES;
     uint8_t* sW2 = smem + SMEM_W2;
     float* sBias = reinterpret_cast<float*>(smem + (FUSE ? SMEM_BIAS_F : SMEM_BIAS));
+    float* sIn = sBias + 2 * BIAS_SLOT / 4;
     constexpr int BAR_OFF = FUSE ? SMEM_BAR_F : SMEM_BAR;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + NBAR * 8);
@@ -385,8 +387,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     // the live row count may sit in device memory (alive-row compaction of the rollout): rows beyond
     // it are not computed; strides still use the allocated N
     const long long n_rows = p.n_dev ? *p.n_dev : p.N;
-    const long long n_units = ((n_rows + 127) / 128) * n_groups;
-    const long long u0 = n_units * blockIdx.x / gridDim.x, u1 = n_units * (blockIdx.x + 1) / gridDim.x;
+    const long long n_units = ((n_rows + 127) / 128) * n_groups;      // < 2^31 (checked by the host)
+    const int u0 = (int)(n_units * blockIdx.x / gridDim.x), u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
 
     // (The pool is the CTA's own allocation of 640 x 96 registers: the 128 x (96 - 32) released by the
     // control warpgroup are exactly the 4 x 128 x 16 the epilogue warpgroups request; asking for more
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         uint32_t s = 0, ph = 0;
         unsigned long long c_wempty = 0;
         const long long t_begin = DBG ? clock64() : 0;
-        for (long long u = u0; u < u1; ++u) {
+        for (int u = u0; u < u1; ++u) {
             {
                 const int e = (int)(u % n_groups);
                 const uint8_t* src = p.wmain + (unsigned long long)e * p.main_bytes;
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         // ===== layer-2 weight producer: the W2 tiles of `cps` consecutive chunks per slot =====
         uint32_t s2 = 0, ph2 = 0, mb = 0;
         unsigned long long dummy = 0;
-        for (long long u = u0; u < u1; ++u, ++mb) {
+        for (int u = u0; u < u1; ++u, ++mb) {
             {
                 const int e = (int)(u % n_groups);
                 {   // hidden-layer biases [b0 | b1] of this unit -> bias buffer (mb & 1)
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         const uint64_t dW2 = smem_desc_sw128(smem_u32(sW2));
         uint32_t s2 = 0, ph2 = 0, c1 = 0, m = 0;
         unsigned long long c_w2 = 0, c_h2 = 0, c_out = 0;
-        for (long long u = u0; u < u1; ++u) {
+        for (int u = u0; u < u1; ++u) {
             int jin = 0;
             for (int jj = 0; jj < NC; ++jj) {
                 // barrier pair = chunk parity (one per epilogue pair), also when H2 is single buffered:
@@ -503,12 +505,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         // included, so that no warp-level election / reconvergence sits between two batches of MMAs
         // (-6% on the 512-wide ensemble).  Grouped narrow members have short batches and are paced by
         // the drains; there the warp-uniform loop with a per-batch election measured 5% faster. =====
-        #ifdef CMBPO_NO_SINGLE
-        constexpr bool SINGLE = false;
-#else
-        constexpr bool SINGLE = (G == 1);
-#endif
-        const uint32_t idesc_h = idesc_f16(FMT, 64), idesc_h2 = idesc_f16(FMT, 128);
+                constexpr bool SINGLE = (G == 1);
+        const uint32_t idesc_h = idesc_f16(FMT, 64);
         // the tensor-memory base as a RUN-TIME value (it is 0, checked above): with a compile-time base ptxas
         // folds the chained operand addresses of mma_f16_ts_tiles back into one constant + R2UR per MMA
         const uint32_t tmem_rt = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
@@ -520,7 +518,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         auto next_stage = [&]() { if (++s == NSM) { s = 0; ph ^= 1; } };
         if (!SINGLE || elect_one()) {
         int cur_tile = -1;
-        for (long long u = u0; u < u1; ++u) {
+        for (int u = u0; u < u1; ++u) {
             const int tile = (int)(u / n_groups);
             if (tile != cur_tile) {                 // a new row tile: its XA panel must have landed
                 cur_tile = tile;
@@ -531,7 +529,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             {
                 for (int j0 = 0; j0 < NC; j0 += G0) {       // layer 0: D = XA x W0 chunk (G0 chunks per stage)
                     wait_t<DBG>(bar + W_FULL + s, ph, c_w);
-#ifdef CMBPO_L0_SPLIT
 #pragma unroll
                     for (int jj = 0; jj < G0; ++jj) {
                         // one chunk per instruction, buffer = chunk parity: the two epilogue pairs run as
@@ -550,29 +547,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                         TRACE(0, 100 + j0 + jj);
                         g += 1;
                     }
-#else
-#pragma unroll
-                    for (int jj = 0; jj < G0; jj += 2) {
-                        // two chunks per instruction (N = 128 fills both accumulator buffers; their
-                        // tiles are adjacent in the stage): halves this thread's per-chunk bookkeeping,
-                        // which paces the drain-bound layer-0 phase
-                        const uint32_t n = g >> 1;                  // g is even here
-                        wait_t<DBG>(bar + D_EMPTY + 0, (n & 1) ^ 1, c_d);
-                        wait_t<DBG>(bar + D_EMPTY + 1, (n & 1) ^ 1, c_d);
-                        tc_fence_after();
-                        if (SINGLE || elect_one()) {
-                            const uint64_t dB = dW0 + (uint64_t)((s * STAGE + jj * TILE) >> 4);
-                            for (int ks = 0; ks < p.KS0; ++ks)
-                                mma_f16(tmem + COL_D, dXA + 2 * ks, dB + 2 * ks, idesc_h2, ks > 0);
-                            mma_commit(bar + D_FULL + 0);
-                            mma_commit(bar + D_FULL + 1);
-                            if (jj == G0 - 2) mma_commit(bar + W_EMPTY + s);
-                        }
-                        if (!SINGLE) __syncwarp();
-                        TRACE(0, 100 + j0 + jj);
-                        g += 2;
-                    }
-#endif
                     next_stage();
                 }
                 wait_t<DBG>(bar + H1_FULL, m & 1, c_h1);
@@ -626,6 +600,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         int prev_e = 0; long long prev_grow = 0; uint32_t prev_m = 0; bool have_prev = false;
         int prev_tile = 0;
         const int etid = (int)threadIdx.x - 128;                      // 0..511 among the epilogue threads
+        // input scaler -> shared memory (identity when the net has none)
+        if (etid < 64) {
+            sIn[etid] = (p.mu_in && etid < p.K0) ? p.mu_in[etid] : 0.f;
+            sIn[64 + etid] = (p.mu_in && etid < p.K0) ? p.sig_in[etid] : 1.f;
+        }
+        epi_bar();
         FzSmem fsm;
         if (FUSE) {
             fsm = fz_views(smem + SMEM_FZ);
@@ -708,7 +688,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         };
         int cur_tile = -1;
         long long grow = 0;
-        for (long long u = u0; u < u1; ++u) {
+        for (int u = u0; u < u1; ++u) {
             const int tile = (int)(u / n_groups);
             const bool new_tile = tile != cur_tile;
             cur_tile = tile;
@@ -741,27 +721,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                         }
                     }
                 }
-                // XA: this row of the input, scaled (pens/utils.py:156), 16-bit, zero padded to 64
+                // XA: this row of the input, scaled (pens/utils.py:156), 16-bit, zero padded to 64.  All global
+                // loads of a 16-column batch are issued before the first use (one L2 round trip per 16 columns; the
+                // earlier 8-column loop with the scaler vectors in global memory cost ~10 k cycles per row
+                // tile with the MMA issuer waiting: shared memory is carved to the limit, there is no L1).
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    float v[8];
+                for (int h = 0; h < 4; ++h) {
+                    float v[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int k = c * 8 + i;
-                        float t = (p.fold && feed && (k == p.K0 || k == p.K0 + 1)) ? 1.0f : 0.f;
-                        if (k < p.K0 && feed) {
-                            if (FUSE) t = (k < p.fz.O) ? p.fz.cur_obs[grow * p.fz.O + k] : p.fz.pi[grow * p.fz.A + (k - p.fz.O)];
-                            else t = xr[k];
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                    if (h * 16 < p.K0 + 2 * p.fold) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int k = h * 16 + i;
+                            if (k < p.K0 && feed) {
+                                if (FUSE) v[i] = (k < p.fz.O) ? p.fz.cur_obs[grow * p.fz.O + k] : p.fz.pi[grow * p.fz.A + (k - p.fz.O)];
+                                else v[i] = xr[k];
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int k = h * 16 + i;
                             // fast division: the result is rounded to 16 bits right below (the IEEE
                             // version is a subroutine call inside this kernel)
-                            if (p.mu_in) t = __fdividef(__fsub_rn(t, p.mu_in[k]), p.sig_in[k]);
+                            if (k < p.K0 && feed) v[i] = __fdividef(__fsub_rn(v[i], sIn[k]), sIn[64 + k]);
+                            else if (p.fold && feed && (k == p.K0 || k == p.K0 + 1)) v[i] = 1.0f;
                         }
-                        v[i] = t;
                     }
-                    uint4 q;
-                    q.x = Cvt<FMT>::pack(v[0], v[1]); q.y = Cvt<FMT>::pack(v[2], v[3]);
-                    q.z = Cvt<FMT>::pack(v[4], v[5]); q.w = Cvt<FMT>::pack(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(sXA + panel_off(row, c)) = q;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint4 q;
+                        q.x = Cvt<FMT>::pack(v[8 * c], v[8 * c + 1]); q.y = Cvt<FMT>::pack(v[8 * c + 2], v[8 * c + 3]);
+                        q.z = Cvt<FMT>::pack(v[8 * c + 4], v[8 * c + 5]); q.w = Cvt<FMT>::pack(v[8 * c + 6], v[8 * c + 7]);
+                        *reinterpret_cast<uint4*>(sXA + panel_off(row, h * 2 + c)) = q;
+                    }
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -1080,6 +1073,7 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     CMBPO_CHECK(precision == CMBPO_PREC_BF16 || precision == CMBPO_PREC_FP16, "bad precision %d", precision);
     CMBPO_CHECK(net.tc_pack[precision], "tcgen05 weights not packed");
     if (N <= 0) return 0;
+    CMBPO_CHECK((N + 127) / 128 * (int64_t)net.E < (int64_t)1 << 31, "too many rows for one launch");
     const int HD = net.dims[1];
     const OutShape os = out_shape(net.dims[3]);
     TcParams p;
