@@ -45,7 +45,7 @@ class RolloutCfg(C.Structure):
                 ("flags", C.c_int), ("compact_every", C.c_int)]
 
 
-ROLLOUT_NO_COMPACT, ROLLOUT_NO_FUSE, ROLLOUT_NO_STORE = 1, 2, 4
+ROLLOUT_NO_COMPACT, ROLLOUT_FUSE, ROLLOUT_NO_STORE = 1, 2, 4
 
 
 # name -> (restype, argtypes); every symbol include/cmbpo_b200.h declares
@@ -58,6 +58,7 @@ SIGNATURES = {
     "cmbpo_ctx_set_stream": (_i, [_vp, _vp]),
     "cmbpo_ctx_synchronize": (_i, [_vp]),
     "cmbpo_ctx_launch_count": (_i64, [_vp]),
+    "cmbpo_ctx_set_debug": (_i, [_vp, _i, _i]),
     "cmbpo_ctx_profile": (_i, [_vp, _i]),
     "cmbpo_ctx_profile_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_i64), _i]),
     "cmbpo_net_set_weights": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_vp),

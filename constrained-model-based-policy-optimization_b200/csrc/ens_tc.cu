@@ -158,7 +158,6 @@ __device__ __forceinline__ void fused_rows(const FusedStep& f, const FzSmem& sm,
         }
         epi_bar();
         const int NI = RP * O;
-        if (!(f.dbg_skip & 8))
         for (int idx = etid; idx < NI; idx += 512) {
             const int rr = idx & (RP - 1), dim = idx >> sh;
             const int member = sm.member[rr];
@@ -202,7 +201,6 @@ __device__ __forceinline__ void fused_rows(const FusedStep& f, const FzSmem& sm,
             }
         }
         epi_bar();
-        if (!(f.dbg_skip & 16))
         for (int idx = etid; idx < NI; idx += 512) {
             const int rr = idx / O, dim = idx - rr * O;
             if (sm.state[rr] != 1) continue;
@@ -552,13 +550,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 wait_t<DBG>(bar + H1_FULL, m & 1, c_h1);
                 tc_fence_after();
                 TRACE(0, 200);
-                for (int j = 0; j < NC; ++j) {              // layer 1 (+ layer 2 of the previous chunk)
-                    const uint32_t buf = g & 1, n = g >> 1;
-                    wait_t<DBG>(bar + D_EMPTY + buf, (n & 1) ^ 1, c_d);
+                // layer 1.  The accumulator hand-off of chunk j+1 is waited for BEFORE the last stage of chunk j
+                // is issued: the issue of that stage is back-pressured by the tensor pipe anyway, so the latency
+                // of the (normally long satisfied) wait hides behind queued MMAs instead of opening a gap
+                // between two chunks.
+                {
+                    const uint32_t buf0 = g & 1, n0 = g >> 1;
+                    wait_t<DBG>(bar + D_EMPTY + buf0, (n0 & 1) ^ 1, c_d);
                     tc_fence_after();
+                }
+                constexpr bool HOIST = (KP / TPS > 1);      // single-stage chunks (narrow members): wait per chunk
+                for (int j = 0; j < NC; ++j) {
+                    const uint32_t buf = g & 1;
+                    if (!HOIST && j > 0) {
+                        wait_t<DBG>(bar + D_EMPTY + buf, ((g >> 1) & 1) ^ 1, c_d);
+                        tc_fence_after();
+                    }
                     TRACE(0, 300 + j);
                     for (int kq = 0; kq < KP / TPS; ++kq) {
                         wait_t<DBG>(bar + W_FULL + s, ph, c_w);      // TMA completion: no tcgen05 fence needed
+                        if (HOIST && kq == KP / TPS - 1 && j + 1 < NC) {
+                            const uint32_t g1 = g + 1;
+                            wait_t<DBG>(bar + D_EMPTY + (g1 & 1), ((g1 >> 1) & 1) ^ 1, c_d);
+                            tc_fence_after();
+                        }
                         if (SINGLE || elect_one()) {
                             // TPS tiles x 4 K-steps from one asm statement (addresses chained inside, see tc_common.cuh)
                             mma_f16_ts_tiles<TPS>(tmem + COL_D + buf * 64, tmem_rt + COL_H1 + ((j / CPM) * KP + kq * TPS) * 32,
@@ -637,7 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 // consecutive floats per column), then the "last arriver" protocol: the CTA that delivers
                 // the tile's E-th member runs the row math for the tile
                 const FusedStep& f = p.fz;
-                if (mine && !(f.dbg_skip & 32)) {
+                if (mine) {
                     const float* b2 = p.bias + (long long)prev_e * p.bias_stride + 2 * HD;
                     float* dst = f.raw_tiles + ((size_t)prev_tile * p.E + prev_e) * p.Nout * 128 + row;
 #pragma unroll
@@ -646,7 +661,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                         if (i < out_cw && c < p.Nout) __stcg(dst + (size_t)c * 128, __uint_as_float(r[i]) + __ldg(b2 + c));
                     }
                 }
-                if (!(f.dbg_skip & 4)) __threadfence();
+                __threadfence();
                 epi_bar();
                 if (etid == 0) {
                     const int old = atomicAdd(f.tile_cnt + prev_tile, 1);
@@ -655,8 +670,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     *fsm.flag = last;
                 }
                 epi_bar();
-                if (*fsm.flag && !(f.dbg_skip & 1)) {
-                    if (!(f.dbg_skip & 4)) __threadfence();
+                if (*fsm.flag) {
+                    __threadfence();
                     fused_rows(f, fsm, prev_tile, n_rows, etid);
                 }
             } else
@@ -702,7 +717,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     // observation, into the XA panel below.  A tile shared by two CTAs is done by both: same
                     // inputs, same values.
                     const FusedStep& f = p.fz;
-                    if (feed && !(f.dbg_skip & 2)) {
+                    if (feed) {
                         const long long pth = f.row_path ? (long long)f.row_path[grow] : grow;
                         const float v = value_of(f.v, f.rules.B, grow), vc = value_of(f.vc, f.rules.B, grow);
                         const uint8_t pend = f.rules.pending[pth];
@@ -1101,9 +1116,9 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     }
     memset(&p.fz, 0, sizeof(p.fz));
     const int act_sel = net.member_act[0] >= 0 ? 0 : net.acts[0];
-    static const char* dbg_env = getenv("CMBPO_TC_DEBUG");
-    const bool dbg_big = dbg_env && atoi(dbg_env) == 1 && HD == 512 && group == 1 && net.acts[0] == CMBPO_ACT_SWISH;
-    const bool dbg_grp = dbg_env && atoi(dbg_env) == 2 && group == 4 && act_sel == 0;
+    // protocol tracing is switched on per context by cmbpo_ctx_set_debug (tools/tcdbg.py); never by the environment
+    const bool dbg_big = ctx->tc_debug == 1 && HD == 512 && group == 1 && net.acts[0] == CMBPO_ACT_SWISH;
+    const bool dbg_grp = ctx->tc_debug == 2 && group == 4 && act_sel == 0;
     if ((dbg_big || dbg_grp) && precision == CMBPO_PREC_FP16) {
         // protocol timing: per-CTA cycle counters printed once per launch (debug aid, off by default)
         unsigned long long* d;
@@ -1112,8 +1127,7 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
         CUDA_TRY(cudaMemsetAsync(d, 0, dbg_words * 8, ctx->stream));
         p.dbg = d;
         {
-            static const char* to = getenv("CMBPO_TC_TRACE_ONLY");
-            const int count_waits = (to && atoi(to)) ? 0 : 1;
+            const int count_waits = ctx->tc_trace_only ? 0 : 1;
             CUDA_TRY(cudaMemcpyToSymbolAsync(g_tc_count_waits, &count_waits, sizeof(int), 0, cudaMemcpyHostToDevice, ctx->stream));
         }
         if (dbg_big ? launch_tc<512, 0, CMBPO_ACT_SWISH, true>(ctx, p) : launch_tc<512, 0, 0, true, 4>(ctx, p)) return 1;

@@ -549,11 +549,13 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
                             (cfg->uncertainty_mode || cfg->env.term_id != CMBPO_TERM_NO_DONE);
     int cur_gen = 0;
     const int compact_every = cfg->compact_every > 0 ? cfg->compact_every : 2;    // measured: 2 beats 1 and 4 by 2-6 %
-    // Fused step (tcgen05 precisions): policy head in the dynamics kernel's input staging, FakeEnv row math /
-    // sampler rules / ModelBuffer write-out in its epilogue -> two launches per step, and the raw [E,B,2D]
-    // outputs only exist tile by tile in an L2-resident scratch.
+    // Fused step (tcgen05 precisions, opt-in with CMBPO_ROLLOUT_FUSE): policy head in the dynamics kernel's
+    // input staging, FakeEnv row math / sampler rules / ModelBuffer write-out in its epilogue -> two launches per
+    // step, and the raw [E,B,2D] outputs only exist tile by tile in an L2-resident scratch.  Opt-in because the
+    // row math then runs on the GEMM kernel's epilogue warps with the tensor pipe idle: measured 24.6 ms against
+    // 21.9 ms per 100 k x 34-step rollout for the four-launch step.
     const int rp_shift = ens_tc_fused_rp_shift(O);
-    const bool fused = cfg->precision != CMBPO_PREC_FP32 && !(cfg->flags & CMBPO_ROLLOUT_NO_FUSE) && ctx->polnet.loaded &&
+    const bool fused = cfg->precision != CMBPO_PREC_FP32 && (cfg->flags & CMBPO_ROLLOUT_FUSE) && ctx->polnet.loaded &&
                        ens_tc_fusable(dyn) && rp_shift >= 5 && dyn.n_elite <= 8 && A <= CMBPO_MAX_ACT;
     const int64_t ntiles = (B + 127) / 128;
     int* tile_cnt = nullptr;
@@ -614,7 +616,6 @@ extern "C" int cmbpo_rollout(cmbpo_ctx* ctx, const cmbpo_rollout_cfg* cfg, const
             fz.state_eps = bufs->state_eps ? bufs->state_eps + (size_t)t * B * O : nullptr;
             fz.row_path = compacting ? row_path[cur_gen] : nullptr;
             fz.raw_tiles = raw; fz.tile_cnt = tile_cnt; fz.rp_shift = rp_shift;
-            { const char* sk = getenv("CMBPO_FZ_SKIP"); fz.dbg_skip = sk ? atoi(sk) : 0; }   // TEMP probe
             {
                 ProfScope prof(ctx, CMBPO_PROF_DYN);
                 if (ens_forward_tc(ctx, dyn, nullptr, B, nullptr, cfg->precision, nd, &fz)) return 1;

@@ -123,7 +123,6 @@ struct FusedStep {
     float* raw_tiles;               // scratch, see above
     int* tile_cnt;                  // [ntiles] members finished per row tile (returns to 0)
     int rp_shift;                   // rows per row-math pass = 1 << rp_shift (staging budget)
-    int dbg_skip;                   // TEMP probe mask
 };
 
 // accessor of the tile-transposed scratch for one row (same interface as RawDyn / RawStaged)

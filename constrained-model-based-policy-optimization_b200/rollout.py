@@ -61,7 +61,7 @@ class RolloutBuffers:
     def run(self, env_cfg, uncertainty_mode=False, dkl_lim=0.0, seed=0, path_id_base=0,
             max_steps=0, precision=None, flags=0, compact_every=0):
         """cmbpo_rollout: the speculative per-path rollout.  `flags`: L.ROLLOUT_* bits (results do not
-        depend on NO_COMPACT / NO_FUSE; NO_STORE leaves the per-step fields untouched)."""
+        depend on NO_COMPACT / FUSE; NO_STORE leaves the per-step fields untouched)."""
         e = self.engine
         cfg = L.RolloutCfg(self.B, int(path_id_base), self.T, int(max_steps),
                            int(bool(uncertainty_mode)), float(dkl_lim if dkl_lim is not None else 0.0),

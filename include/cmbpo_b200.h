@@ -79,6 +79,10 @@ int64_t cmbpo_ctx_launch_count(cmbpo_ctx* ctx);
  * time and the number of bracketed launches, and optionally resets the slot.
  */
 enum { CMBPO_PROF_DYN = 0, CMBPO_PROF_GAE = 1, CMBPO_PROF_STEP = 2, CMBPO_PROF_POLICY = 3, CMBPO_PROF_SLOTS = 4 };
+/* Developer aid (tools/tcdbg.py): tc_debug 1 / 2 makes the wide / grouped tcgen05 kernel print per-CTA protocol
+ * counters and an event trace to stderr (synchronises); trace_only drops the wait counters.  0 = off (default).
+ * Nothing in the library reads environment variables. */
+int cmbpo_ctx_set_debug(cmbpo_ctx* ctx, int tc_debug, int trace_only);
 int cmbpo_ctx_profile(cmbpo_ctx* ctx, int enable);
 int cmbpo_ctx_profile_read(cmbpo_ctx* ctx, int slot, double* total_ms_host, int64_t* launches_host,
                            int reset);
@@ -187,14 +191,16 @@ typedef struct {
 
 /* cmbpo_rollout_cfg.flags.  None of them changes a result bit (tests compare both settings):
  *   NO_COMPACT  keep finished paths' rows in the batch (see below);
- *   NO_FUSE     tensor-core precisions: run the step as separate launches (policy GEMM, policy rows,
- *               dynamics GEMM with raw [E,B,2D] outputs in HBM, row kernel) instead of the fused step
- *               kernel (policy head in the dynamics kernel's input staging, FakeEnv / sampler rules /
- *               ModelBuffer write-out in its epilogue);
+ *   FUSE        tensor-core precisions: run the step as TWO launches -- the policy GEMM, and the dynamics
+ *               GEMM kernel with the policy head in its input staging and the FakeEnv row math / sampler
+ *               rules / ModelBuffer write-out in its epilogue (raw outputs only tile by tile in an
+ *               L2-resident scratch) -- instead of the default four (policy GEMM, policy rows, dynamics
+ *               GEMM with raw [E,B,2D] outputs in HBM, row kernel).  Bit-identical; opt-in because it is
+ *               currently slower (the row math occupies the GEMM kernel's epilogue warps);
  *   NO_STORE    do not write the per-step ModelBuffer fields (obs .. term may then be NULL): only the
  *               per-path results and step_stats -- ModelSampler.compute_dynamics_dkl
  *               (samplers/model_sampler.py:151-167) = sum_t step_stats[t][1] / sum_t step_stats[t][0]. */
-enum { CMBPO_ROLLOUT_NO_COMPACT = 1, CMBPO_ROLLOUT_NO_FUSE = 2, CMBPO_ROLLOUT_NO_STORE = 4 };
+enum { CMBPO_ROLLOUT_NO_COMPACT = 1, CMBPO_ROLLOUT_FUSE = 2, CMBPO_ROLLOUT_NO_STORE = 4 };
 
 /* Like the reference (model_sampler.py:255-259, 300-311) only alive paths are fed to the networks: on
  * the tensor-core precisions, where paths can end early (termination function / uncertainty mode), the

@@ -1,6 +1,6 @@
 """The fused rollout step (policy head + FakeEnv row math + sampler rules + ModelBuffer write-out inside
 the tcgen05 dynamics kernel, two launches per step) against the step-wise tensor-core path
-(`ROLLOUT_NO_FUSE`: four launches per step, raw [E,B,2D] outputs through HBM).  Both run literally the
+(the default: four launches per step, raw [E,B,2D] outputs through HBM).  Both run literally the
 same per-row functions (csrc/step_common.cuh, row_math.cuh) on the same GEMM results, in the same
 summation order, so every field must be BIT-identical -- whatever parity the step-wise path has with the
 oracle (tests/test_gpu_tc.py, test_gpu_parity_tc.py) the fused path inherits exactly."""
@@ -56,8 +56,8 @@ def test_fused_equals_stepwise_injected_noise(engine, key, B, T, prec):
     obs, act = orc.make_states(302, B, O, A, dyn)
     noise = orc.TableNoise(303, T, B, A, len(dyn.elite_inds))
     cfg = env.env_cfg(True)
-    fused = _run(engine, cfg, B, T, O, A, obs, noise, 0, prec)
-    step = _run(engine, cfg, B, T, O, A, obs, noise, L.ROLLOUT_NO_FUSE, prec)
+    fused = _run(engine, cfg, B, T, O, A, obs, noise, L.ROLLOUT_FUSE, prec)
+    step = _run(engine, cfg, B, T, O, A, obs, noise, 0, prec)
     assert fused.launches < step.launches, (fused.launches, step.launches)
     if key == "hcs":                                   # no terminations: no compaction launches
         assert fused.launches <= 2 * (T - 1) + 6, fused.launches
@@ -80,10 +80,10 @@ def test_fused_equals_stepwise_philox_uncertainty(engine, key, hidden, B):
     lim = calibrated_dkl_lim(dyn, task, obs[:2000], act[:2000], factor=12.0)
     cfg = env.env_cfg(True)
     kw = dict(uncertainty_mode=True, dkl_lim=lim, seed=5)
-    ref = _run(engine, cfg, B, T, O, A, obs, None, L.ROLLOUT_NO_FUSE | L.ROLLOUT_NO_COMPACT, "fp16", **kw)
+    ref = _run(engine, cfg, B, T, O, A, obs, None, L.ROLLOUT_NO_COMPACT, "fp16", **kw)
     ln = ref.length.cpu().numpy()
     assert 1 < ln.mean() < T - 2 and len(np.unique(ln)) > 5
-    for flags in (0, L.ROLLOUT_NO_COMPACT, L.ROLLOUT_NO_FUSE):
+    for flags in (L.ROLLOUT_FUSE, L.ROLLOUT_FUSE | L.ROLLOUT_NO_COMPACT, 0):
         got = _run(engine, cfg, B, T, O, A, obs, None, flags, "fp16", **kw)
         # final_obs of ended paths is whatever row the compaction left behind: compare alive paths only
         _assert_identical(engine, got, ref, skip=("final_obs",))
@@ -102,8 +102,8 @@ def test_fused_state_noise_mode(engine):
     noise = orc.TableNoise(323, T, B, A, len(dyn.elite_inds))
     noise.state_eps = rng.standard_normal((T, B, O)).astype(np.float32)
     for nz in (noise, None):                                      # injected arrays, then Philox
-        fused = _run(engine, cfg, B, T, O, A, obs, nz, 0, "fp16", seed=9)
-        step = _run(engine, cfg, B, T, O, A, obs, nz, L.ROLLOUT_NO_FUSE, "fp16", seed=9)
+        fused = _run(engine, cfg, B, T, O, A, obs, nz, L.ROLLOUT_FUSE, "fp16", seed=9)
+        step = _run(engine, cfg, B, T, O, A, obs, nz, 0, "fp16", seed=9)
         _assert_identical(engine, fused, step)
 
 

@@ -1,4 +1,4 @@
-"""TEMP: cost of the pieces of the fused step kernel (CMBPO_FZ_SKIP mask), K1F ms per launch."""
+"""Fused (two launches per step) against the default four-launch rollout step: ms per rollout and per launch."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -14,10 +14,9 @@ pol = cb.B200Policy(eng); pol.load_actor(actor.W, actor.b, actor.log_std); pol.l
 obs, act = wl.make_states(1, B, O, A, dyn)
 cfg = L.EnvCfg(L.TERM_NO_DONE, L.COST_HCS, 0, 1, 1)
 bufs = cb.RolloutBuffers(eng, B, T, O, A); bufs.set_inputs(obs)
-masks = [int(x) for x in sys.argv[1:]] or [0, 1, 1 | 2, 1 | 4, 1 | 2 | 4 | 32, 8, 16, 8 | 16, 4]
-for flags, name in ((0, "fused"), (L.ROLLOUT_NO_FUSE, "stepwise")):
-    for m in (masks if flags == 0 else [0]):
-        os.environ["CMBPO_FZ_SKIP"] = str(m)
+masks = [0]
+for flags, name in ((L.ROLLOUT_FUSE, "fused"), (0, "stepwise")):
+    for m in (masks if flags else [0]):
         for i in range(2):
             bufs.run(cfg, seed=i, flags=flags)
         eng.profile(True); eng.profile_read(0, True); eng.profile_read(3, True); eng.profile_read(2, True)

@@ -10,6 +10,7 @@ from cmbpo_b200 import workload as orc   # synthetic problem generator (no test 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 dyn, actor, v, vc = orc.make_problem(0, 17, 6, hidden=(512, 512))
 eng = cb.Engine(0, precision="fp16")
+L.check(eng.lib.cmbpo_ctx_set_debug(eng.h, int(os.environ.get("CMBPO_TC_DEBUG", "0")), int(os.environ.get("CMBPO_TC_TRACE_ONLY", "0"))))
 policy = cb.B200Policy(eng)
 policy.load_actor(actor.W, actor.b, actor.log_std)
 policy.load_values(v, vc)
