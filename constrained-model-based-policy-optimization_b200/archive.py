@@ -37,11 +37,12 @@ class DeviceArchive:
     # ---- filling (CPOBuffer.dump_to_archive, cpobuffer.py:209-247) ---------------------------
     def append(self, observations, mu, log_std, epochs):
         """Rows of one or more epochs, written at the ring pointer like dump_to_archive: when they
-        do not fit, the pointer wraps to 0 and the oldest rows are overwritten."""
+        do not fit (or fit exactly -- the reference's `>=`), the pointer wraps to 0 and the oldest rows are
+        overwritten."""
         e, t = self.engine, self.engine.torch
         n = len(observations)
         assert n <= self.archive_size
-        if self.archive_ptr + n > self.archive_size:
+        if self.archive_ptr >= self.archive_size - n:      # cpobuffer.py:221: an exact fit wraps too
             self.archive_ptr = 0
         sl = slice(self.archive_ptr, self.archive_ptr + n)
         self.observations[sl] = e.to_device(np.asarray(observations, np.float32), t.float32)

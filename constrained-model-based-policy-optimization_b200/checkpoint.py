@@ -80,6 +80,12 @@ def read_pe_checkpoint(model_dir, name, timestep):
     else:
         raise ValueError("%s: last layer width %d vs described %d" % (stem, last, layers[-1][0]))
     d_out = last // 2 if probabilistic else last
+    # The .nns last-layer activation is the reference's `end_act`, which a probabilistic net applies to the
+    # MEAN half only, after unsetting the layer activation (pe.py:183-185, 817-818).  The kernels have no
+    # mean-only output activation, so refuse it rather than apply it to the log-variance half as well.
+    if probabilistic and acts[-1] not in (None, "None", "none", "linear"):
+        raise ValueError("%s: output_activation %r on a probabilistic ensemble is not supported "
+                         "(the reference applies it to the mean half only)" % (stem, acts[-1]))
     scal = [a.reshape(1, -1) for a in arrs[:n_scal]]
     mu_in = var_in = mu_out = var_out = None
     if n_scal == 4:

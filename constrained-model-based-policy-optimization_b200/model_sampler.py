@@ -73,6 +73,8 @@ class ModelSampler:
 
     # ---- calibration (model_sampler.py:151-167) ----------------------------------------------
     def compute_dynamics_dkl(self, obs_batch, depth=1):
+        if self.fused:
+            return self._dynamics_dkl_device(obs_batch, depth)
         for _ in range(depth):
             outs = self.policy.get_action_outs(obs_batch)
             next_obs, _, terminal, info = self.env.step(obs_batch, outs["pi"])
@@ -80,6 +82,29 @@ class ModelSampler:
             self._total_dkl += info.get("ensemble_dkl_mean", 0) * n_paths
             self._total_samples += n_paths
             obs_batch = next_obs[np.squeeze(~terminal)]
+        return self.dyn_dkl * depth
+
+    def _dynamics_dkl_device(self, obs_batch, depth):
+        """The same quantity from one `depth`-step device rollout that stores nothing (CMBPO_ROLLOUT_NO_STORE):
+        step_stats[t] = (rows fed, sum of their disagreement, ..) so that
+        sum_t mean_t * n_t = sum_t step_stats[t][1] and the sample count is sum_t step_stats[t][0]; rows of
+        terminated paths leave the batch between steps as in the reference loop."""
+        from .rollout import RolloutBuffers
+        env = self.env
+        eng = env.engine
+        on_device = hasattr(obs_batch, "is_cuda") and obs_batch.is_cuda
+        obs = obs_batch if on_device else np.asarray(obs_batch, np.float32)
+        depth = int(depth)
+        assert depth >= 1 and obs.shape[0] > 0
+        bufs = RolloutBuffers(eng, obs.shape[0], depth + 1, env.obs_dim, env.act_dim, lean=True)
+        inj = self.injected or {}
+        bufs.set_inputs(obs, inj.get("act_eps"), inj.get("elite_pos"), inj.get("state_eps"))
+        self._dkl_calls = getattr(self, "_dkl_calls", 0) + 1
+        bufs.run(env.env_cfg(True), uncertainty_mode=False, seed=(self.seed << 20) + (1 << 19) + self._dkl_calls,
+                 path_id_base=self.path_id_base, max_steps=depth)
+        st = bufs.step_stats.cpu().numpy()[:depth]
+        self._total_dkl += float(st[:, 1].sum())
+        self._total_samples += int(st[:, 0].sum())
         return self.dyn_dkl * depth
 
     # ---- reset (model_sampler.py:203-237) ----------------------------------------------------
@@ -116,7 +141,9 @@ class ModelSampler:
         bufs = pool.bufs
         inj = self.injected or {}
         bufs.set_inputs(observations, inj.get("act_eps"), inj.get("elite_pos"), inj.get("state_eps"))
-        steps = min(self._max_path_length, pool.max_path_length) - 1
+        # a path ends once path_length >= max_path_length - 1 AFTER a store (model_sampler.py:352): the
+        # reference stores max(1, H - 1) steps per path, also for H = 1 (schedule mode with min_length 1)
+        steps = max(1, min(self._max_path_length, pool.max_path_length) - 1)
         bufs.run(env.env_cfg(True), uncertainty_mode=(self.rollout_mode == "uncertainty"),
                  dkl_lim=self.dkl_lim if self.dkl_lim is not None else 0.0,
                  seed=(self.seed << 20) + self._resets, path_id_base=self.path_id_base,

@@ -232,8 +232,13 @@ class ModelBuffer:
         resets.  Returns a handle whose `result()` waits for the copies and returns exactly what
         `get()` returns.  At most two handles may be outstanding (two pinned buffer sets)."""
         self._pin_gen = getattr(self, "_pin_gen", 0) ^ 1
-        out, diag = self.get_device(staging_gen=self._pin_gen)
         t, dev = self.engine.torch, self.engine.device
+        # the staging / pinned buffers of this generation may still be read by the copy of the handle
+        # issued two calls ago: the compaction kernels below must not start before that copy finished
+        prev = self.__dict__.setdefault("_gen_done", {}).get(self._pin_gen)
+        if prev is not None:
+            t.cuda.current_stream(dev).wait_event(prev)
+        out, diag = self.get_device(staging_gen=self._pin_gen)
         ls_row = out[10][:1].cpu().numpy().reshape(1, -1) if out[10].shape[0] else np.zeros((1, self.act_dim), np.float32)
         ls_host = np.broadcast_to(ls_row, tuple(out[10].shape))
         if getattr(self, "_copy_stream", None) is None:
@@ -259,6 +264,7 @@ class ModelBuffer:
                 host.append(h)
             done = t.cuda.Event()
             done.record(self._copy_stream)
+        self._gen_done[self._pin_gen] = done
         self.reset()
         return PendingGet(done, host, ls_host, diag, out)
 

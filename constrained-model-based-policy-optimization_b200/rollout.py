@@ -18,15 +18,19 @@ GAE_FIELDS = ("adv", "ret", "cadv", "cret")
 
 
 class RolloutBuffers:
-    def __init__(self, engine, B, T, obs_dim, act_dim):
+    def __init__(self, engine, B, T, obs_dim, act_dim, lean=False):
+        """`lean`: only the per-path results and the per-step statistics (for CMBPO_ROLLOUT_NO_STORE runs:
+        the per-step ModelBuffer fields stay NULL)."""
         t = engine.torch
         self.engine, self.B, self.T, self.O, self.A = engine, int(B), int(T), int(obs_dim), int(act_dim)
+        self.lean = bool(lean)
         z = engine.zeros
-        self.obs, self.nextobs = z(T, B, obs_dim), z(T, B, obs_dim)
-        self.act, self.mu = z(T, B, act_dim), z(T, B, act_dim)
-        for k in STEP_FIELDS + GAE_FIELDS:
-            setattr(self, k, z(T, B))
-        self.term = z(T, B, dtype=t.uint8)
+        if not lean:
+            self.obs, self.nextobs = z(T, B, obs_dim), z(T, B, obs_dim)
+            self.act, self.mu = z(T, B, act_dim), z(T, B, act_dim)
+            for k in STEP_FIELDS + GAE_FIELDS:
+                setattr(self, k, z(T, B))
+            self.term = z(T, B, dtype=t.uint8)
         self.length = z(B, dtype=t.int32)
         self.end_reason = z(B, dtype=t.uint8)
         self.last_val, self.last_cval = z(B), z(B)
@@ -43,7 +47,7 @@ class RolloutBuffers:
             tns = getattr(self, name, None)
             setattr(s, name, None if tns is None else tns.data_ptr())
         # keep dtype discipline explicit
-        assert self.length.dtype == e.torch.int32 and self.term.dtype == e.torch.uint8
+        assert self.length.dtype == e.torch.int32 and (self.lean or self.term.dtype == e.torch.uint8)
         return s
 
     def set_inputs(self, start_obs, act_eps=None, elite_pos=None, state_eps=None):
@@ -63,6 +67,8 @@ class RolloutBuffers:
         """cmbpo_rollout: the speculative per-path rollout.  `flags`: L.ROLLOUT_* bits (results do not
         depend on NO_COMPACT / FUSE; NO_STORE leaves the per-step fields untouched)."""
         e = self.engine
+        if self.lean:
+            flags = int(flags) | L.ROLLOUT_NO_STORE
         cfg = L.RolloutCfg(self.B, int(path_id_base), self.T, int(max_steps),
                            int(bool(uncertainty_mode)), float(dkl_lim if dkl_lim is not None else 0.0),
                            int(seed), e._prec(precision), env_cfg, int(flags), int(compact_every))

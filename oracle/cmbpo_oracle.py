@@ -587,6 +587,22 @@ class OracleModelSampler:
     def _ids(self):
         return np.flatnonzero(self.pool.alive_paths)
 
+    def compute_dynamics_dkl(self, obs_batch, depth=1):               # :151-167
+        """Mean ensemble disagreement over `depth` model steps from `obs_batch`, times depth; the rows of
+        terminated paths are dropped between steps.  Needs reset() first (the accumulators of :203-237)."""
+        obs_batch = np.asarray(obs_batch)
+        ids = np.arange(obs_batch.shape[0])
+        for step in range(depth):
+            self.policy.ctx = self.env.ctx = (step, ids)
+            a = self.policy.get_action_outs(obs_batch)["pi"]
+            next_obs, _, terminal, info = self.env.step(obs_batch, a)
+            n_paths = next_obs.shape[0]
+            self.total_dkl += info.get("ensemble_dkl_mean", 0) * n_paths
+            self.total_samples += n_paths
+            keep = np.squeeze(~terminal, -1) if terminal.ndim > 1 else ~terminal
+            obs_batch, ids = next_obs[keep], ids[keep]
+        return self.total_dkl / (self.total_samples + SAMPLER_EPS) * depth
+
     def sample(self, max_samples=None):                               # :239-375
         pool = self.pool
         assert pool.has_room and self.obs is not None and pool.alive_paths.any()
