@@ -104,16 +104,30 @@ def test_rollout_vs_golden(engine, key):
     want_pop = z["snap_populated"]
     same = (pop == want_pop).all(1)
     assert same.mean() >= 0.95                      # threshold flips only within float noise of a limit
+    len_g, len_w = pop.sum(1), want_pop.sum(1)
     out, diag = pool.get()
     if same.all():
         assert diag["poolm_batch_size"] == int(z["poolm_batch_size"])
-        for i in range(12):
-            w = z["out%d" % i]
-            assert out[i].shape == w.shape and out[i].dtype == w.dtype, i
-            if i == 9:
-                assert (out[i] != w).mean() < 0.02
+    # never vacuous: the rows of the agreeing paths are compared whatever happened to the others
+    # (get() is path-major: path p owns len[p] consecutive rows)
+    sel_g, sel_w = np.repeat(same, len_g), np.repeat(same, len_w)
+    assert sel_g.sum() == sel_w.sum() > 0
+    for i in range(12):
+        w = z["out%d" % i]
+        assert out[i].dtype == w.dtype and out[i].shape[1:] == w.shape[1:], i
+        assert out[i].shape[0] == len_g.sum() and w.shape[0] == len_w.sum(), i
+        g_, w_ = out[i][sel_g], w[sel_w]
+        if i == 9:
+            assert (g_ != w_).mean() < 0.02
+        elif i in (2, 3):
+            # normalised advantages: the batch mean / std include the flipped paths (mpi_statistics_scalar over
+            # the whole batch), so they only agree tightly when every path agrees
+            if same.all():
+                assert np.allclose(g_, w_, rtol=5e-3, atol=5e-3), i
             else:
-                assert np.allclose(out[i], w, rtol=5e-3, atol=5e-3), i
+                assert np.corrcoef(g_.ravel(), w_.ravel())[0, 1] > 0.999, i
+        else:
+            assert np.allclose(g_, w_, rtol=5e-3, atol=5e-3), i
 
 
 def test_philox_shard_invariance(engine):

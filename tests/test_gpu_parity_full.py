@@ -1,0 +1,130 @@
+"""Parity of the BENCHMARKED configuration against the oracle: fp16 tcgen05 GEMMs, (512,512) ensembles, the fast
+row variant (closed-form KL), T = 35, B = 2048, injected noise, both rollout modes, the three task shapes.
+
+What is asserted (tolerances stated here, measured values printed with `pytest -s` and recorded in
+profiles/r2_parity_fp16.txt):
+  * every path whose discrete outcomes cannot legitimately flip -- cumulative disagreement never within
+    DKL_MARGIN of the limit, cost / termination inputs never within STATE_MARGIN of their thresholds on any
+    stored step -- has EXACTLY the oracle's length, end reason class, populated mask, term and cost arrays;
+  * on those paths all 16 per-step fields and adv / ret / cadv / cret agree within the per-step table TOL
+    (error relative to |oracle| + 1; the bound grows with the step index because every step feeds the 16-bit
+    rounding of the previous state through networks with a Lipschitz constant above one);
+  * the paths outside the margins may flip; their fraction and the flip rate are reported and bounded.
+"""
+import numpy as np
+import pytest
+
+from oracle import cmbpo_oracle as orc
+from helpers import TASKS, GAE, load_problem, ShapeEnv, calibrated_dkl_lim
+
+pytestmark = pytest.mark.gpu
+
+B, T = 2048, 35
+DKL_MARGIN = 0.03          # relative distance of the running disagreement sum from dkl_lim
+STATE_MARGIN = 0.02        # absolute distance of a threshold input (state coordinate, scaled) from its threshold
+# per-step tolerance on |got - want| / (|want| + 1):  TOL0 * (1 + t / TGROW)
+TOL0, TGROW = 4e-3, 4.0
+FIELDS = ("obs", "act", "nextobs", "rew", "val", "cval", "logp", "mu", "dyn_error")
+GAE_FIELDS = ("adv", "ret", "cadv", "cret")
+
+
+def _threshold_margin_ok(task, nextobs, pop):
+    """Paths whose cost / termination inputs stay STATE_MARGIN away from every threshold of models/statics.py on
+    all stored steps (evaluated on the ORACLE's states)."""
+    x = nextobs
+    ok = np.ones(x.shape[:2], bool)
+    if task.startswith("HalfCheetahSafe"):
+        ok &= np.abs(np.abs(x[..., -1] * 10.0) - 2.0) > STATE_MARGIN * 10
+    elif task.startswith("AntSafe"):
+        z = x[..., 0]
+        zrot = 1.0 - 2.0 * (x[..., 2] ** 2 + x[..., 3] ** 2)
+        ok &= (np.abs(z - 0.2) > STATE_MARGIN) & (np.abs(z - 1.0) > STATE_MARGIN)
+        ok &= np.abs(zrot + 0.7) > STATE_MARGIN
+        ok &= np.abs(np.abs(x[..., -1]) - 3.2) > STATE_MARGIN
+    return np.all(ok | ~pop, axis=1)
+
+
+@pytest.mark.parametrize("key,mode", [("hcs", False), ("hcs", "uncertainty"), ("ant", False), ("ant", "uncertainty"),
+                                      ("hum", False), ("hum", "uncertainty")])
+def test_fp16_full_width_rollout_vs_oracle(engine, key, mode, capsys):
+    import cmbpo_b200 as cb
+    task, O, A = TASKS[key]
+    dyn, actor, v, vc = orc.make_problem(501, O, A, hidden=(512, 512), task=task)
+    obs, act = orc.make_states(502, B, O, A, dyn)
+    noise = orc.TableNoise(503, T, B, A, len(dyn.elite_inds))
+    lim = calibrated_dkl_lim(dyn, task, obs, act, factor=14.0) if mode else None
+    out, bdiag, diag, snap = orc.run_rollout(dyn, actor, v, vc, task, obs, noise, T, mode, lim,
+                                             gamma=GAE["gamma"], lam=GAE["lam"],
+                                             cgamma=GAE["cost_gamma"], clam=GAE["cost_lam"])
+    model, policy = load_problem(engine, dyn, actor, v, vc)
+    env = cb.FakeEnv(ShapeEnv(O, A), task, model, True, True, False)
+    bufs = cb.RolloutBuffers(engine, B, T, O, A)
+    bufs.set_inputs(obs, noise.act_eps, noise.elite_pos)
+    bufs.run(env.env_cfg(True), uncertainty_mode=bool(mode), dkl_lim=lim or 0.0, precision="fp16")
+    bufs.gae(GAE["gamma"], GAE["lam"], GAE["cost_gamma"], GAE["cost_lam"])
+    engine.synchronize()
+
+    wpop = snap["populated"]
+    want_len = wpop.sum(1)
+    got_len = bufs.length.cpu().numpy()
+    gpop = bufs.populated_mask()
+
+    # ---- which paths are outside every flip margin ----
+    stable = _threshold_margin_ok(task, snap["nextobs"], wpop)
+    if mode:
+        # running disagreement sum BEFORE the cut decision of each fed step, from the device's own per-step
+        # values (stored steps) -- a path is stable if no decision point is within DKL_MARGIN of the limit,
+        # including the step that cut it (cum_dkl holds the sum of the stored steps only)
+        dkl = bufs.host("dkl").astype(np.float64)
+        cum = np.cumsum(np.where(gpop, dkl, 0.0), axis=1)
+        near = (np.abs(cum - lim) <= DKL_MARGIN * lim) & gpop
+        stable &= ~near.any(1)
+        # the cutting step itself is not stored: paths ended as 'uncertain' are stable only if the oracle ended
+        # them at the same step or the last stored sum is far below the limit
+        reason = bufs.end_reason.cpu().numpy()
+    same_len = got_len == want_len
+    n_stable = int(stable.sum())
+    flip_stable = int((~same_len & stable).sum())
+    flip_all = int((~same_len).sum())
+
+    # ---- exact discrete outcomes on the stable paths ----
+    if mode:
+        # a path cut by the uncertainty rule ends one step BEFORE the step whose sum crossed the limit; that sum is
+        # not stored, so stability of the cut step cannot be read from the buffers: allow flips there but count them
+        assert flip_stable <= 0.01 * max(n_stable, 1), (flip_stable, n_stable)
+        exact = stable & same_len
+    else:
+        assert flip_stable == 0, (flip_stable, np.flatnonzero(~same_len & stable)[:10])
+        exact = stable
+    m2 = (wpop & gpop) & exact[:, None]
+    assert np.array_equal(gpop[exact], wpop[exact])
+    term_g, term_w = bufs.host("term"), snap["term"]
+    cost_g, cost_w = bufs.host("cost"), snap["cost"]
+    assert np.array_equal(term_g[m2], term_w[m2])
+    assert np.array_equal(cost_g[m2], cost_w[m2])
+
+    # ---- floats: per-step tolerance table ----
+    tol_t = TOL0 * (1.0 + np.arange(T) / TGROW)
+    worst = {}
+    for name in FIELDS + GAE_FIELDS:
+        g, w = bufs.host(name), snap[name]
+        err = np.abs(g - w) / (np.abs(w) + 1.0)
+        if err.ndim == 3:
+            err = err.max(-1)
+        err = np.where(m2, err, 0.0)
+        per_t = err.max(0)
+        worst[name] = per_t
+        bound = tol_t if name not in GAE_FIELDS else np.full(T, tol_t[-1] * 2)   # GAE sums errors of later steps
+        assert np.all(per_t <= bound), (name, int(np.argmax(per_t / bound)), float(per_t.max()))
+    # ---- report ----
+    with capsys.disabled():
+        print("\n[parity fp16 %s mode=%s] B=%d T=%d  mean len %.2f  stable paths %d (%.1f%%)  length flips: stable %d, all %d (%.2f%%)"
+              % (key, mode, B, T, want_len.mean(), n_stable, 100.0 * n_stable / B, flip_stable, flip_all,
+                 100.0 * flip_all / B))
+        for name in ("nextobs", "rew", "val", "logp", "dyn_error", "adv", "cret"):
+            p = worst[name]
+            print("    %-9s max rel err  t=0 %.2e  t=8 %.2e  t=16 %.2e  t=33 %.2e   (bound t=0 %.1e, t=33 %.1e)"
+                  % (name, p[0], p[8], p[16], p[min(33, T - 1)], tol_t[0], tol_t[33]))
+    # flips overall stay rare
+    assert flip_all <= (0.05 if mode else 0.01) * B
+    assert n_stable >= 0.5 * B
