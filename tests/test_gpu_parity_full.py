@@ -23,7 +23,7 @@ B, T = 2048, 35
 DKL_MARGIN = 0.03          # relative distance of the running disagreement sum from dkl_lim
 STATE_MARGIN = 0.02        # absolute distance of a threshold input (state coordinate, scaled) from its threshold
 # per-step tolerance on |got - want| / (|want| + 1):  TOL0 * (1 + t / TGROW)
-TOL0, TGROW = 4e-3, 4.0
+TOL0, TGROW = 1.5e-3, 6.0      # measured worst: 6e-4 at t = 0, 6.3e-3 at t = 33 (HCS value head)
 FIELDS = ("obs", "act", "nextobs", "rew", "val", "cval", "logp", "mu", "dyn_error")
 GAE_FIELDS = ("adv", "ret", "cadv", "cret")
 
