@@ -37,6 +37,20 @@ MAXROLL = 35
 GAE = dict(gamma=0.99, lam=0.95, cost_gamma=0.97, cost_lam=0.5)
 METRIC, UNIT = "model-rollout transitions/sec", "transitions/s"
 WORKLOAD = ("BASELINE configs[1]: HalfCheetahSafe H-step model rollout + GAE/cost-GAE + advantage normalisation")
+# BASELINE.json configs[1..4]; the default line is configs[1]
+TASKS = {"hcs": ("HalfCheetahSafe-v2", 17, 6), "ant": ("AntSafe-v2", 29, 8), "hum": ("HumanoidSafe-v2", 47, 17)}
+CONFIGS = {
+    "hcs": dict(task="hcs", workload=WORKLOAD, scaling="weak"),
+    "ant1m": dict(task="ant", scaling="strong", total=1000000,
+                  workload="BASELINE configs[2]: AntSafe ensemble rollout, 1M start states sharded over the ranks "
+                           "(termination function shortens paths; alive-row compaction) + GAE/cost-GAE + normalisation"),
+    "hs_gae": dict(task="hum", scaling="weak",
+                   workload="BASELINE configs[3]: HumanoidSafe (configs/cmbpo_hs) rollout feeding the GAE + cost-GAE "
+                            "reverse scans; standalone GAE layouts in `gae_layouts`"),
+    "sweep": dict(task="hcs", scaling="strong",
+                  workload="BASELINE configs[4]: HalfCheetahSafe roofline sweep, horizon H x total start states B "
+                           "(sharded over the ranks)"),
+}
 
 
 _REAL_STDOUT = None
@@ -82,12 +96,26 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes per launch of K1 from the committed `ncu --set full` summary (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_k1_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f)["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    for name in ("r2_k1_traffic.json", "r1_k1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
+
+
+def ncu_tensor_pipe():
+    """sm__pipe_tensor_cycles_active (% of elapsed) of K1 from the committed ncu summary, or None."""
+    for name in ("r2_k1_ncu.txt", "r1_k1_ncu.txt"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                for ln in f:
+                    if ln.startswith("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"):
+                        return {"value": float(ln.split()[-1].replace(",", "")), "source": "profiles/" + name}
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -208,6 +236,23 @@ def cpu_rollout_sample(B, seed=0):
     return len(out[0]), dt
 
 
+def cpu_single_step(n_rows, seed=0):
+    """BASELINE configs[0]: one FakeEnv.step (predict_ensemble + average_dkl + statics) on n_rows synthetic
+    (obs17, act6) rows through the oracle port; rows per second."""
+    from oracle import cmbpo_oracle as orc
+    dyn, actor, v, vc = orc.make_problem(seed, OBS, ACT, hidden=HIDDEN, task=TASK)
+    obs, act = orc.make_states(seed + 1, n_rows, OBS, ACT, dyn)
+    noise = orc.TableNoise(seed + 2, 2, n_rows, ACT, len(dyn.elite_inds))
+    env = orc.OracleFakeEnv(OBS, ACT, TASK, orc.OracleModel(dyn), noise.idx_fn)
+    env.ctx = (0, np.arange(256))
+    env.step(obs[:256], act[:256])
+    env.ctx = (0, np.arange(n_rows))
+    t0 = time.perf_counter()
+    env.step(obs, act)
+    dt = time.perf_counter() - t0
+    return n_rows / dt, dt
+
+
 def cpu_gae_ms_per_1m():
     from oracle import cmbpo_oracle as orc
     rng = np.random.default_rng(0)
@@ -224,7 +269,7 @@ def run_reference(args, rank, world):
         return
     cores = host_threads()
     B = args.cpu_batch
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    for _ in range(args.warmup):                      # W warm-up passes (small: BLAS thread pools, page faults)
         cpu_rollout_sample(min(B, 200))
     times, n_tr = [], 0
     for s in range(args.steps):
@@ -253,101 +298,192 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
+class Rig:
+    """One rank's engine with the synthetic networks of a task shape loaded (weights generated on rank 0 and
+    broadcast once over NCCL, then uploaded from device memory)."""
+
+    def __init__(self, task_key, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        import cmbpo_b200 as cb
+        from cmbpo_b200 import _lib as L
+        from cmbpo_b200 import workload as wl
+        self.torch, self.dist, self.cb, self.L, self.wl = torch, dist, cb, L, wl
+        self.rank, self.world, self.local_rank, self.args = rank, world, local_rank, args
+        self.task, self.O, self.A = TASKS[task_key]
+        self.dev = torch.device("cuda", local_rank)
+        self.eng = cb.Engine(local_rank, precision=args.precision)
+        self.dyn, self.actor, self.v, self.vc = wl.make_problem(0, self.O, self.A, hidden=HIDDEN, task=self.task)
+        dev = self.dev
+
+        def bcast(a):
+            x = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+            if world > 1:
+                if rank != 0:
+                    x.zero_()
+                dist.broadcast(x, 0)
+            return x
+
+        def ens_dev(en):
+            return dict(W=[bcast(w) for w in en.W], b=[bcast(b) for b in en.b], mu_in=bcast(en.mu_in),
+                        var_in=bcast(en.var_in), mu_out=bcast(en.mu_out), var_out=bcast(en.var_out))
+
+        self.dev_nets = {L.NET_DYN: ens_dev(self.dyn), L.NET_V: ens_dev(self.v), L.NET_VC: ens_dev(self.vc)}
+        self.dev_actor = ([bcast(w) for w in self.actor.W], [bcast(b) for b in self.actor.b], bcast(self.actor.log_std))
+        self.load_engine(self.eng)
+        term = L.TERM_ANTSAFE if task_key == "ant" else L.TERM_NO_DONE
+        cost = {"hcs": L.COST_HCS, "ant": L.COST_ANTSAFE, "hum": L.COST_ZERO}[task_key]
+        # --mode mean: deterministic-mean transitions (what ModelSampler runs, model_sampler.py:259);
+        # --mode injected: mean + std * eps with Philox eps per (path, step, dim) (SURVEY.md 8a-Q1)
+        self.env_cfg = L.EnvCfg(term, cost, 0, 0 if args.mode == "injected" else 1, 1)
+
+    def load_engine(self, e):
+        L = self.L
+        for which, en, prob in ((L.NET_DYN, self.dyn, True), (L.NET_V, self.v, False), (L.NET_VC, self.vc, False)):
+            d = self.dev_nets[which]
+            e.set_network(which, d["W"], d["b"], en.acts, d["mu_in"], d["var_in"], d["mu_out"],
+                          d["var_out"], prob, en.elite_inds)
+        e.set_actor(*self.dev_actor)
+
+    def reduce_fn(self, x):
+        if self.world > 1:
+            self.dist.all_reduce(x)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flops(self, h=HIDDEN[0]):
+        O, A = self.O, self.A
+        D, Din = O + 1, O + A
+        dyn = 2 * E * (Din * h + h * h + h * 2 * D)
+        actor = 2 * (O * 128 + 128 * 128 + 128 * A)
+        vvc = 2 * 3 * 2 * (O * 128 + 128 * 128 + 128)
+        return dyn, actor, vvc
+
+    def row_bytes(self):
+        return (2 * self.O + 3 * self.A + 6) * 4 + 2          # SURVEY.md 8d: write-out bytes per stored transition
+
+    def timed_rollouts(self, B, T, steps, warmup, seed0=1234, with_stats=True):
+        """`steps` passes of rollout -> GAE -> statistics -> normalise over B device-resident start states.
+        Returns dict(ms, n_tr (whole job), launches, dyn_launch_ms, gae_launch_ms, breakdown, clocks)."""
+        torch, eng, L = self.torch, self.eng, self.L
+        obs_host, _ = self.wl.make_states(100 + self.rank, B, self.O, self.A, self.dyn)
+        start = torch.from_numpy(obs_host).to(self.dev)
+        bufs = self.cb.RolloutBuffers(eng, B, T, self.O, self.A)
+        path_base = self.rank * B
+        world = self.world
+
+        def hot_path(step):
+            bufs.start_obs = start
+            bufs.run(self.env_cfg, seed=seed0 + step, path_id_base=path_base, precision=self.args.precision,
+                     flags=(L.ROLLOUT_FUSE if self.args.fuse else 0))
+            bufs.gae(GAE["gamma"], GAE["lam"], GAE["cost_gamma"], GAE["cost_lam"])
+            sums = eng.adv_statistics_device(bufs.adv, bufs.cadv, bufs.ret, bufs.cret, B, T, 1, B, bufs.length,
+                                             self.reduce_fn if world > 1 else None)
+            eng.adv_normalise_device(bufs.adv, bufs.cadv, B, T, 1, B, bufs.length, sums)
+            return sums
+
+        for w in range(warmup):
+            hot_path(-1 - w)
+        self.barrier()
+        eng.profile(True)
+        for k in range(4):
+            eng.profile_read(k, True)
+        clocks = ClockSampler(self.local_rank)
+        clocks.start()
+        launches0 = eng.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        n_acc = torch.zeros(1, device=self.dev, dtype=torch.float64)
+        for s_ in range(steps):
+            n_acc += hot_path(s_)[0:1]    # with N > 1 the statistics are all-reduced: already the whole-job count
+        ev1.record()
+        self.barrier()
+        clk = clocks.stop()
+        ms = ev0.elapsed_time(ev1)
+        n_tr = float(n_acc.item())
+        res = dict(ms=ms, n_tr=n_tr, launches=eng.launch_count - launches0, clocks=clk, obs_host=obs_host)
+        for name, k in (("dyn", L_PROF_DYN), ("gae", L_PROF_GAE), ("step", 2), ("pol", 3)):
+            t_ms, n = eng.profile_read(k, True)
+            res[name + "_ms"], res[name + "_n"] = t_ms, n
+        eng.profile(False)
+        del bufs
+        return res
+
+    def reduce_result(self, res, extra_max=(), extra_sum=()):
+        """max over ranks of the times, sum of the counts"""
+        torch = self.torch
+        vec = torch.tensor([res["ms"], res["dyn_ms"] / max(res["dyn_n"], 1), res["gae_ms"] / max(res["gae_n"], 1)] + list(extra_max),
+                           device=self.dev, dtype=torch.float64)
+        cnt = torch.tensor([res["n_tr"], res["launches"]] + list(extra_sum), device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(vec, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(cnt, op=self.dist.ReduceOp.SUM)
+            cnt[0] /= self.world          # n_tr was global on every rank
+        return [float(x) for x in vec], [float(x) for x in cnt]
+
+
+def roofline_obj(pk, flop_per_row, rows_per_launch, launch_ms, step_ms, launches_per_pass, kernel_name):
+    ach = flop_per_row * rows_per_launch / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+    tp = ncu_tensor_pipe()
+    return {"bound": "tensor", "kernel": kernel_name, "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+            "frac": ach / pk["tf_burst"], "frac_burst": ach / pk["tf_burst"], "frac_sustained": ach / pk["tf_sus"],
+            "peak_sustained": pk["tf_sus"],
+            "peak_note": "%s bf16 GEMM peaks of MEASURED_PEAKS.json; `frac` is against the BURST figure (the timed "
+                         "region is < 1 s at full clocks), frac_sustained against the 4 s / power-capped one" % pk["src"],
+            "tensor_pipe_active_pct_ncu": tp, "traffic": ncu_traffic(),
+            "launch_ms": launch_ms, "rows_per_launch": rows_per_launch, "flop_per_row": flop_per_row,
+            "share_of_step": launch_ms * launches_per_pass / step_ms if step_ms > 0 else None}
+
+
+def dtype_name(precision):
+    return {"fp32": "f32", "fp16": "f16 (tcgen05 kind::f16, f32 accumulate)",
+            "bf16": "bf16 (tcgen05 kind::f16, f32 accumulate)"}[precision]
+
+
+def mode_name(args):
+    return ("injected-noise (mean + std*eps, Philox eps)" if args.mode == "injected" else "deterministic-mean") + \
+        ", Philox action noise / elite draws, dkl_lim=inf"
+
+
 def run_cuda(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    import cmbpo_b200 as cb
-    from cmbpo_b200 import _lib as L
-    from cmbpo_b200 import workload as wl      # synthetic weights / start states (no oracle on this arm)
-
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    eng = cb.Engine(local_rank, precision=args.precision)
-    t = torch
-
-    # weights: generated on rank 0, broadcast once over NCCL (NVLink), then uploaded from device
-    dyn, actor, v, vc = wl.make_problem(0, OBS, ACT, hidden=HIDDEN, task=TASK)
-
-    def bcast(a):
-        x = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = CONFIGS[args.config]
+    rig = Rig(cfg["task"], args, rank, world, local_rank)
+    try:
+        {"hcs": bench_hcs, "ant1m": bench_ant1m, "hs_gae": bench_hs_gae, "sweep": bench_sweep}[args.config](rig, args, cfg)
+    finally:
         if world > 1:
-            if rank != 0:
-                x.zero_()
-            dist.broadcast(x, 0)
-        return x
+            dist.destroy_process_group()
+        rig.eng.close()
 
-    def ens_dev(en):
-        return dict(W=[bcast(w) for w in en.W], b=[bcast(b) for b in en.b], mu_in=bcast(en.mu_in),
-                    var_in=bcast(en.var_in), mu_out=bcast(en.mu_out), var_out=bcast(en.var_out))
 
-    dev_nets = {L.NET_DYN: ens_dev(dyn), L.NET_V: ens_dev(v), L.NET_VC: ens_dev(vc)}
-    dev_actor = ([bcast(w) for w in actor.W], [bcast(b) for b in actor.b], bcast(actor.log_std))
+def base_line(rig, args, cfg, value, ms_per_step, extra_config):
+    c = {"workload": cfg["workload"], "maxroll": MAXROLL, "stored_steps": MAXROLL - 1, "obs": rig.O, "act": rig.A,
+         "ensemble": "7x(512,512) swish, 5 elites", "policy": "tanh 128-128 + 2x(3x swish 128-128-1)",
+         "mode": mode_name(args), "precision": args.precision,
+         "step": "fused (CMBPO_ROLLOUT_FUSE: 2 launches per step)" if args.fuse else "step-wise (4 launches per step)"}
+    c.update(extra_config)
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": rig.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"],
+            "vs_baseline": None, "dtype": dtype_name(args.precision), "data": "synthetic", "config": c}
 
-    def load_engine(e):
-        for which, en, prob in ((L.NET_DYN, dyn, True), (L.NET_V, v, False), (L.NET_VC, vc, False)):
-            d = dev_nets[which]
-            e.set_network(which, d["W"], d["b"], en.acts, d["mu_in"], d["var_in"], d["mu_out"],
-                          d["var_out"], prob, en.elite_inds)
-        e.set_actor(*dev_actor)
 
-    load_engine(eng)
-
+# ---- configs[1]: the default line ----------------------------------------------------------------
+def bench_hcs(rig, args, cfg):
+    torch, cb, L, eng = rig.torch, rig.cb, rig.L, rig.eng
+    world, rank, dev = rig.world, rig.rank, rig.dev
     B, T = args.batch, MAXROLL
-    obs_host, _ = wl.make_states(100 + rank, B, OBS, ACT, dyn)
-    obs_pinned = torch.from_numpy(obs_host).pin_memory()
-    start_dev = obs_pinned.to(dev)
-    bufs = cb.RolloutBuffers(eng, B, T, OBS, ACT)
-    env_cfg = L.EnvCfg(L.TERM_NO_DONE, L.COST_HCS, 0, 1, 1)
+    res = rig.timed_rollouts(B, T, args.steps, args.warmup)
+    obs_host = res["obs_host"]
     path_base = rank * B
-
-    def reduce_fn(x):
-        if world > 1:
-            dist.all_reduce(x)
-
-    def hot_path(step, start):
-        """rollout -> GAE -> statistics -> normalise, everything resident in HBM."""
-        bufs.start_obs = start
-        bufs.run(env_cfg, seed=1234 + step, path_id_base=path_base, precision=args.precision)
-        bufs.gae(GAE["gamma"], GAE["lam"], GAE["cost_gamma"], GAE["cost_lam"])
-        st = eng.adv_statistics(bufs.adv, bufs.cadv, bufs.ret, bufs.cret, B, T, 1, B, bufs.length,
-                                reduce_fn if world > 1 else None)
-        eng.adv_normalise(bufs.adv, bufs.cadv, B, T, 1, B, bufs.length, st)
-        return st
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for w in range(args.warmup):
-        hot_path(-1 - w, start_dev)
-    barrier()
-
-    # ---- timed region (device-resident inputs) ----
-    eng.profile(True)
-    eng.profile_read(L_PROF_DYN, True); eng.profile_read(L_PROF_GAE, True)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    n_tr = 0
-    for s in range(args.steps):
-        st = hot_path(s, start_dev)
-        n_tr += st["n"]          # with N > 1 the statistics are all-reduced: already the whole-job count
-    ev1.record()
-    barrier()
-    clk = clocks.stop()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count - launches0
-    dyn_ms, dyn_n = eng.profile_read(L_PROF_DYN, True)
-    gae_ms, gae_n = eng.profile_read(L_PROF_GAE, True)
-    step_ms, step_n = eng.profile_read(2, True)
-    pol_ms, pol_n = eng.profile_read(3, True)
-    eng.profile(False)
 
     # ---- end to end through the public API: host start states in, host sample list out ----
     class _Space:
@@ -355,38 +491,53 @@ def run_cuda(args, rank, world, local_rank):
             self.shape = (n,)
 
     class ShapeEnv:
-        observation_space, action_space = _Space(OBS), _Space(ACT)
+        observation_space, action_space = _Space(rig.O), _Space(rig.A)
 
-    # Two sampler / buffer pairs, each on its own engine (= its own CUDA stream), used alternately as a
-    # caller would to keep the GPU busy: reset() only queues the rollout, so batch i+1 rolls out while
-    # the host walks batch i through sample() / finish_all_paths() / get_async() and while the
-    # device->host copy of batch i runs on a side stream.  Every batch's H2D (start states) and D2H
-    # (sample list) are inside the timed region.
     def make_pair(k):
         stream = torch.cuda.current_stream(dev) if k == 0 else torch.cuda.Stream(device=dev)
         with torch.cuda.stream(stream):
-            e = eng if k == 0 else cb.Engine(local_rank, precision=args.precision)
+            e = eng if k == 0 else cb.Engine(rig.local_rank, precision=args.precision)
             if k:
-                load_engine(e)
+                rig.load_engine(e)
             policy = cb.B200Policy(e)
-            policy.attach_loaded(actor.log_std)
-            fenv = cb.FakeEnv(ShapeEnv(), TASK, cb.B200PE.view(e, L.NET_DYN), True, True, False)
-            pool = cb.ModelBuffer(B, OBS, ACT, T, engine=e)
-            pool.initialize({"mu": (ACT,), "log_std": (ACT,)}, **GAE)
-            pool.reduce_fn = reduce_fn if world > 1 else None
+            policy.attach_loaded(rig.actor.log_std)
+            fenv = cb.FakeEnv(ShapeEnv(), rig.task, cb.B200PE.view(e, L.NET_DYN), True, True, False)
+            pool = cb.ModelBuffer(B, rig.O, rig.A, T, engine=e)
+            pool.initialize({"mu": (rig.A,), "log_std": (rig.A,)}, **GAE)
+            pool.reduce_fn = rig.reduce_fn if world > 1 else None
             smp = cb.ModelSampler(T, B, False, logger=object(), seed=7 + k)
             smp.path_id_base = path_base
             smp.initialize(fenv, policy, pool)
         return smp, pool, stream
 
-    pairs = [make_pair(0), make_pair(1)]
-    torch.cuda.synchronize()
+    def d2h_bytes(out):
+        # bytes that crossed PCIe: a stride-0 axis (log_std, one row broadcast) is not copied
+        return sum(int(np.prod([m for m, st in zip(a.shape, a.strides) if st != 0] or [1])) * a.itemsize for a in out)
 
-    def e2e_reset(k):
+    # (1) `e2e`: the unmodified caller's sequence (algorithms/cmbpo.py:251-269): reset -> sample until the alive
+    # ratio drops -> finish_all_paths -> get(), one sampler / buffer pair, blocking get() that returns caller-owned
+    # numpy arrays.
+    def plain_batch(pair):
+        smp, pool, _ = pair
+        smp.reset(obs_host)
+        while True:
+            _, _, _, info = smp.sample(None)
+            if info["alive_ratio"] <= 0.1:
+                break
+        smp.finish_all_paths()
+        out, _ = pool.get()
+        return out
+
+    # (2) `e2e_pipelined`: two sampler / buffer pairs, each on its own engine (= its own CUDA stream), used
+    # alternately: reset() only queues the rollout, so batch i+1 rolls out while the host walks batch i through
+    # sample() / finish_all_paths() / get_async() and while the device->host copy of batch i runs on a side
+    # stream.  get_async() is an extension of the reference interface; its arrays are views of recycled
+    # page-locked buffers (valid until the second next get_async of that buffer).
+    def e2e_reset(pairs, k):
         with torch.cuda.stream(pairs[k][2]):
             pairs[k][0].reset(obs_host)              # H2D of the start states, rollout queued
 
-    def e2e_collect(k):
+    def e2e_collect(pairs, k):
         smp, pool, stream = pairs[k]
         with torch.cuda.stream(stream):
             while True:
@@ -396,99 +547,263 @@ def run_cuda(args, rank, world, local_rank):
             smp.finish_all_paths()
             return pool.get_async()
 
-    def e2e_run(n_batches):
-        n, d2h, handles = 0, 0, []
-        e2e_reset(0)
+    def pipelined_run(pairs, n_batches):
+        n, handles, out = 0, [], None
+        e2e_reset(pairs, 0)
         for i in range(n_batches):
             if i + 1 < n_batches:
-                e2e_reset((i + 1) & 1)
-            handles.append(e2e_collect(i & 1))
+                e2e_reset(pairs, (i + 1) & 1)
+            handles.append(e2e_collect(pairs, i & 1))
             if len(handles) == 2:                    # at most two sample lists in flight
                 out, _ = handles.pop(0).result()
                 n += len(out[0])
         for h in handles:
             out, _ = h.result()
             n += len(out[0])
-        # bytes that crossed PCIe: a stride-0 axis (log_std, one row broadcast) is not copied
-        d2h = sum(int(np.prod([m for m, st in zip(a.shape, a.strides) if st != 0] or [1])) * a.itemsize for a in out)
-        return n, d2h
+        return n, d2h_bytes(out)
 
-    e2e_run(4)              # warm-up: page-locked buffer sets of both pairs get allocated
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 10))
-    e2e_n, d2h = e2e_run(e2e_steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e = e2e_pipe = None
+    plain_n = pipe_n = 0
+    plain_s = pipe_s = 1.0
+    d2h_plain = d2h_pipe = 0
+    if not args.no_e2e:
+        pairs = [make_pair(0), make_pair(1)]
+        torch.cuda.synchronize()
+        for _ in range(max(2, min(args.warmup, 3))):
+            plain_batch(pairs[0])
+        rig.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = plain_batch(pairs[0])
+            plain_n += len(out[0])
+        rig.barrier()
+        plain_s = time.perf_counter() - t0
+        d2h_plain = d2h_bytes(out)
+        del out
+        pipelined_run(pairs, 4)             # warm-up: page-locked buffer sets of both pairs get allocated
+        rig.barrier()
+        t0 = time.perf_counter()
+        pipe_n, d2h_pipe = pipelined_run(pairs, args.steps)
+        rig.barrier()
+        pipe_s = time.perf_counter() - t0
 
-    # ---- max over ranks / totals ----
-    vec = torch.tensor([ms, e2e_s, dyn_ms / max(dyn_n, 1), gae_ms / max(gae_n, 1)], device=dev, dtype=torch.float64)
-    cnt = torch.tensor([n_tr, e2e_n, launches], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        cnt[0] /= world          # n_tr was global on every rank (see the timed loop)
-    ms, e2e_s, dyn_launch_ms, gae_launch_ms = (float(x) for x in vec)
-    n_tr, e2e_n, launches = (float(x) for x in cnt)
-
-    if rank == 0:
-        pk = peaks()
-        fdyn, fact, fvvc = flop_per_transition()
-        rows_per_launch = B                      # every dynamics launch processes all B rows of one step
-        achieved_tf = fdyn * rows_per_launch / (dyn_launch_ms * 1e-3) / 1e12 if dyn_launch_ms > 0 else 0.0
-        tensor_path = args.precision != "fp32"
-        peak_tf = pk["tf_sus"]
-        gae_steps = B * (T - 1)
-        gae_gbs = 32.0 * gae_steps / (gae_launch_ms * 1e-3) / 1e9 if gae_launch_ms > 0 else 0.0
-        # CPU baseline: bounded sample of the same workload through the oracle port
-        # CPU baseline: rank 0 at N=1 only (under torchrun OMP_NUM_THREADS is pinned to 1)
-        skip_cpu = world > 1 or args.cpu_batch <= 0        # --cpu-batch 0: developer runs only
-        cpu_n, cpu_dt = (0, 1.0) if skip_cpu else cpu_rollout_sample(args.cpu_batch)
-        if not skip_cpu and cpu_dt < 6.0:                         # scale the bounded sample to ~12 s of CPU work
+    (ms, dyn_launch_ms, gae_launch_ms, plain_s, pipe_s), (n_tr, launches, plain_n, pipe_n) = \
+        rig.reduce_result(res, extra_max=(plain_s, pipe_s), extra_sum=(plain_n, pipe_n))
+    if rank != 0:
+        return
+    pk = peaks()
+    fdyn, fact, fvvc = rig.flops()
+    gae_steps = B * (T - 1)
+    gae_gbs = 32.0 * gae_steps / (gae_launch_ms * 1e-3) / 1e9 if gae_launch_ms > 0 else 0.0
+    # CPU baseline: rank 0 at N=1 only (under torchrun OMP_NUM_THREADS is pinned to 1)
+    skip_cpu = world > 1 or args.cpu_batch <= 0        # --cpu-batch 0: developer runs only
+    cpu = None
+    if not skip_cpu:
+        cpu_n, cpu_dt = cpu_rollout_sample(args.cpu_batch)
+        if cpu_dt < 6.0:                                # scale the bounded sample to ~12 s of CPU work
             scaled = int(min(20000, args.cpu_batch * 12.0 / max(cpu_dt, 1e-3)))
             cpu_n, cpu_dt = cpu_rollout_sample(scaled)
             args.cpu_batch = scaled
-        cores = host_threads()
-        line = {
-            "metric": METRIC, "value": n_tr / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "fp16": "f16 (tcgen05 kind::f16, f32 accumulate)",
-                      "bf16": "bf16 (tcgen05 kind::f16, f32 accumulate)",
-                      }[args.precision],
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "start_states_per_gpu": B, "maxroll": T, "stored_steps": T - 1, "obs": OBS, "act": ACT,
-                       "ensemble": "7x(512,512) swish, 5 elites", "policy": "tanh 128-128 + 2x(3x swish 128-128-1)",
-                       "mode": "deterministic-mean, Philox noise, dkl_lim=inf", "precision": args.precision,
-                       "l2": "rollout buffers (%.0f MB/GPU) exceed the 126 MB L2; no explicit flush" %
-                             (B * T * ((2 * OBS + 2 * ACT + 11) * 4 + 1) / 1e6),
-                       "flop_per_transition": fdyn + fact + fvvc,
-                       "peak_note": "tensor peak = %s bf16 GEMM, sustained (burst %.1f)" % (pk["src"], pk["tf_burst"])},
-            "roofline": {"bound": "tensor", "kernel": "dynamics-ensemble GEMM chain (K1)",
-                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if tensor_path else achieved_tf / peak_tf,
-                         "traffic": ncu_traffic(), "launch_ms": dyn_launch_ms, "rows_per_launch": rows_per_launch,
-                         "flop_per_row": fdyn, "share_of_step": dyn_launch_ms * (T - 1) / (ms / args.steps)},
-            "gae": {"ms_per_1M_steps": gae_launch_ms / (gae_steps / 1e6), "achieved_GBps": gae_gbs,
-                    "peak_GBps": pk["hbm"], "frac": gae_gbs / pk["hbm"], "bytes_per_step": 32,
-                    "steps_per_launch": gae_steps, "scan": "strict float64 sequential (bit-exact)"},
-            "cpu_baseline": ({"value": cpu_n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
-                              "sample": "%d start states x %d steps (one pass, %.1f s)" % (args.cpu_batch, T - 1, cpu_dt)}
-                             if not skip_cpu else None),
-            "e2e": {"value": e2e_n / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(obs_host.nbytes), "d2h_bytes_per_step": int(d2h),
-                    "api": "ModelSampler.reset/sample/finish_all_paths + ModelBuffer.get_async().result(), numpy in / numpy out, two sampler+buffer pairs alternating (batch i+1 rolls out while batch i is collected and copied)"},
-            "breakdown_ms_per_step": {"dynamics_gemm_chain": dyn_ms / args.steps, "policy_pass": pol_ms / args.steps,
-                                      "row_kernel": step_ms / args.steps, "gae": gae_ms / args.steps,
-                                      "note": "rank 0, CUDA events around each launch"},
-            "gpu_launches": int(launches),
-            "clocks": clk,
-        }
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
-    eng.close()
+        rows_s, rows_dt = cpu_single_step(10000)
+        cpu = {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": host_threads(), "kind": "port",
+               "sample": "%d start states x %d steps (one pass, %.1f s)" % (args.cpu_batch, T - 1, cpu_dt),
+               "single_step": {"rows_per_s": rows_s, "rows": 10000, "seconds": rows_dt,
+                               "what": "BASELINE configs[0]: one FakeEnv.step (predict_ensemble + KL + statics) on 10k "
+                                       "(obs17, act6) rows, oracle port"}}
+    line = base_line(rig, args, cfg, n_tr / (ms * 1e-3), ms / args.steps, {
+        "start_states_per_gpu": B,
+        "l2": "rollout buffers (%.0f MB/GPU) exceed the 126 MB L2; no explicit flush" %
+              (B * T * ((2 * rig.O + 2 * rig.A + 11) * 4 + 1) / 1e6),
+        "flop_per_transition": fdyn + fact + fvvc})
+    line["roofline"] = roofline_obj(pk, fdyn, B, dyn_launch_ms, ms / args.steps, T - 1, "dynamics-ensemble GEMM chain (K1)")
+    line["gae"] = {"ms_per_1M_steps": gae_launch_ms / (gae_steps / 1e6), "achieved_GBps": gae_gbs,
+                   "peak_GBps": pk["hbm"], "frac": gae_gbs / pk["hbm"], "bytes_per_step": 32,
+                   "steps_per_launch": gae_steps, "scan": "strict float64 sequential (bit-exact)"}
+    line["cpu_baseline"] = cpu
+    if not args.no_e2e:
+        line["e2e"] = {"value": plain_n / plain_s, "unit": UNIT, "h2d_bytes_per_step": int(obs_host.nbytes),
+                       "d2h_bytes_per_step": int(d2h_plain), "batches": args.steps,
+                       "api": "the unmodified caller's sequence (cmbpo.py:251-269): ModelSampler.reset / sample / "
+                              "finish_all_paths + blocking ModelBuffer.get(), numpy in, caller-owned numpy out, one pair"}
+        line["e2e_pipelined"] = {"value": pipe_n / pipe_s, "unit": UNIT, "h2d_bytes_per_step": int(obs_host.nbytes),
+                                 "d2h_bytes_per_step": int(d2h_pipe), "batches": args.steps,
+                                 "api": "two sampler+buffer pairs alternating with ModelBuffer.get_async().result() "
+                                        "(extension: views of recycled page-locked buffers); batch i+1 rolls out while "
+                                        "batch i is collected and copied"}
+    else:
+        line["e2e"] = None
+    line["breakdown_ms_per_step"] = {"dynamics_gemm_chain": res["dyn_ms"] / args.steps, "policy_pass": res["pol_ms"] / args.steps,
+                                     "row_kernel": res["step_ms"] / args.steps, "gae": res["gae_ms"] / args.steps,
+                                     "note": "rank 0, CUDA events around each launch"}
+    line["gpu_launches"] = int(launches)
+    line["clocks"] = res["clocks"]
+    emit(line)
+
+
+# ---- configs[2]: AntSafe, 1M start states sharded (strong scaling) -----------------------------------
+def bench_ant1m(rig, args, cfg):
+    world = rig.world
+    total = args.total if args.total > 0 else cfg["total"]
+    B, T = total // world, MAXROLL
+    res = rig.timed_rollouts(B, T, args.steps, args.warmup)
+    (ms, dyn_launch_ms, gae_launch_ms), (n_tr, launches) = rig.reduce_result(res)
+    if rig.rank != 0:
+        return
+    pk = peaks()
+    fdyn, fact, fvvc = rig.flops()
+    line = base_line(rig, args, cfg, n_tr / (ms * 1e-3), ms / args.steps, {
+        "start_states_total": B * world, "start_states_per_gpu": B,
+        "mean_path_length": n_tr / args.steps / (B * world),
+        "l2": "rollout buffers far exceed the 126 MB L2; no explicit flush",
+        "flop_per_transition": fdyn + fact + fvvc})
+    # rows per dynamics launch vary (alive-row compaction): the achieved rate uses the FLOPs of the rows that were
+    # stored (= useful work) over the summed launch time
+    useful = fdyn * (n_tr / world) / (res["dyn_ms"] * 1e-3) / 1e12 if res["dyn_ms"] > 0 else 0.0
+    line["roofline"] = {"bound": "tensor", "kernel": "dynamics-ensemble GEMM chain (K1), all launches of the pass",
+                        "achieved": useful, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": useful / pk["tf_burst"],
+                        "frac_burst": useful / pk["tf_burst"], "frac_sustained": useful / pk["tf_sus"], "traffic": None,
+                        "note": "useful FLOPs (stored transitions of rank 0) / summed K1 time of rank 0; rows of paths "
+                                "that ended since the last compaction are computed and discarded"}
+    line["writeout_GBps"] = rig.row_bytes() * n_tr / (ms * 1e-3) / 1e9
+    line["cpu_baseline"] = None
+    line["e2e"] = None
+    line["breakdown_ms_per_step"] = {"dynamics_gemm_chain": res["dyn_ms"] / args.steps, "policy_pass": res["pol_ms"] / args.steps,
+                                     "row_kernel": res["step_ms"] / args.steps, "gae": res["gae_ms"] / args.steps}
+    line["gpu_launches"] = int(launches)
+    line["clocks"] = res["clocks"]
+    emit(line)
+
+
+# ---- configs[3]: HumanoidSafe rollout -> GAE, plus the standalone GAE layouts of SURVEY.md 8d -------------
+def gae_layouts(rig):
+    """Standalone GAE + cost-GAE timings (CUDA events, 20 launches after 3 warm-ups), ms per 1M steps and GB/s
+    at 32 B/step: ModelBuffer layout full / ragged, CPOBuffer flat layout, and the amortised 64M-step launch."""
+    torch, eng, L = rig.torch, rig.eng, rig.L
+    g = torch.Generator(device=rig.dev)
+    g.manual_seed(1)
+    out = {}
+
+    def rnd(*shape):
+        return torch.randn(*shape, device=rig.dev, generator=g)
+
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def paths_case(name, B, T, ragged):
+        r, v, c, cv = rnd(T, B), rnd(T, B), (torch.rand(T, B, device=rig.dev, generator=g) < 0.1).float(), rnd(T, B)
+        length = (torch.randint(1, T, (B,), device=rig.dev, generator=g) if ragged
+                  else torch.full((B,), T - 1, device=rig.dev)).to(torch.int32)
+        lv, lc = rnd(B), rnd(B)
+        outs = tuple(torch.zeros(T, B, device=rig.dev) for _ in range(4))
+        steps = int(length.sum().item())
+        ms = timeit(lambda: eng.gae_paths(r, v, c, cv, length, lv, lc, GAE["gamma"], GAE["lam"], GAE["cost_gamma"],
+                                          GAE["cost_lam"], B, T, 1, B, out=outs))
+        out[name] = {"steps": steps, "ms": ms, "ms_per_1M_steps": ms / (steps / 1e6), "GBps": 32.0 * steps / (ms * 1e-3) / 1e9}
+
+    paths_case("modelbuffer_32768x35_full", 32768, 35, False)
+    paths_case("modelbuffer_32768x35_ragged", 32768, 35, True)
+    paths_case("amortised_64M_steps", 1900000, 35, False)
+    # CPOBuffer flat layout: 1049 paths x 1000 steps (warp-shuffle segmented scan)
+    n_seg, seg = 1049, 1000
+    n = n_seg * seg
+    r, v, cv = rnd(n), rnd(n), rnd(n)
+    c = (torch.rand(n, device=rig.dev, generator=g) < 0.1).float()
+    off = torch.arange(0, n + 1, seg, device=rig.dev, dtype=torch.int64)
+    lv, lc = rnd(n_seg), rnd(n_seg)
+    outs = tuple(torch.zeros(n, device=rig.dev) for _ in range(4))
+    for nm, scan in (("cpobuffer_flat_1049x1000_warp", L.SCAN_WARP), ("cpobuffer_flat_1049x1000_strict", L.SCAN_STRICT)):
+        ms = timeit(lambda: eng.gae_flat(r, v, c, cv, off, lv, lc, GAE["gamma"], GAE["lam"], GAE["cost_gamma"],
+                                         GAE["cost_lam"], out=outs, scan=scan))
+        out[nm] = {"steps": n, "ms": ms, "ms_per_1M_steps": ms / (n / 1e6), "GBps": 32.0 * n / (ms * 1e-3) / 1e9}
+    return out
+
+
+def bench_hs_gae(rig, args, cfg):
+    B, T = args.batch, MAXROLL
+    res = rig.timed_rollouts(B, T, args.steps, args.warmup)
+    (ms, dyn_launch_ms, gae_launch_ms), (n_tr, launches) = rig.reduce_result(res)
+    layouts = gae_layouts(rig) if rig.rank == 0 else None
+    rig.barrier()
+    if rig.rank != 0:
+        return
+    pk = peaks()
+    fdyn, fact, fvvc = rig.flops()
+    gae_steps = B * (T - 1)
+    gae_gbs = 32.0 * gae_steps / (gae_launch_ms * 1e-3) / 1e9 if gae_launch_ms > 0 else 0.0
+    line = base_line(rig, args, cfg, n_tr / (ms * 1e-3), ms / args.steps, {
+        "start_states_per_gpu": B, "l2": "rollout buffers exceed the 126 MB L2; no explicit flush",
+        "flop_per_transition": fdyn + fact + fvvc})
+    line["roofline"] = roofline_obj(pk, fdyn, B, dyn_launch_ms, ms / args.steps, T - 1, "dynamics-ensemble GEMM chain (K1)")
+    line["roofline"]["traffic"] = None
+    line["roofline"]["tensor_pipe_active_pct_ncu"] = None
+    line["gae"] = {"ms_per_1M_steps": gae_launch_ms / (gae_steps / 1e6), "achieved_GBps": gae_gbs, "peak_GBps": pk["hbm"],
+                   "frac": gae_gbs / pk["hbm"], "bytes_per_step": 32, "steps_per_launch": gae_steps,
+                   "scan": "strict float64 sequential (bit-exact), in the rollout pass"}
+    for k in layouts.values():
+        k["frac_hbm"] = k["GBps"] / pk["hbm"]
+    line["gae_layouts"] = layouts
+    line["writeout_GBps"] = rig.row_bytes() * n_tr / (ms * 1e-3) / 1e9
+    line["cpu_baseline"] = None
+    line["e2e"] = None
+    line["breakdown_ms_per_step"] = {"dynamics_gemm_chain": res["dyn_ms"] / args.steps, "policy_pass": res["pol_ms"] / args.steps,
+                                     "row_kernel": res["step_ms"] / args.steps, "gae": res["gae_ms"] / args.steps}
+    line["gpu_launches"] = int(launches)
+    line["clocks"] = res["clocks"]
+    emit(line)
+
+
+# ---- configs[4]: H x B sweep -------------------------------------------------------------------------------
+def bench_sweep(rig, args, cfg):
+    world = rig.world
+    pk = peaks()
+    fdyn, fact, fvvc = rig.flops()
+    Hs = [int(x) for x in args.sweep_h.split(",")]
+    Bs = [int(x) for x in args.sweep_b.split(",")]
+    cells, launches_total, clk = [], 0, None
+    for Btot in Bs:
+        B = max(1, Btot // world)
+        for H in Hs:
+            steps = max(2, min(args.steps, int(2e8 / max(B * H, 1)) + 2))       # small cells: more repetitions
+            res = rig.timed_rollouts(B, H + 1, steps, max(1, min(args.warmup, 2)))
+            (ms, dyn_launch_ms, gae_launch_ms), (n_tr, launches) = rig.reduce_result(res)
+            launches_total += launches
+            clk = res["clocks"]
+            tr_s = n_tr / (ms * 1e-3)
+            k1 = fdyn * B / (dyn_launch_ms * 1e-3) / 1e12 if dyn_launch_ms > 0 else 0.0
+            cells.append({"H": H, "B_total": B * world, "B_per_gpu": B, "passes": steps, "transitions_per_s": tr_s,
+                          "ms_per_pass": ms / steps, "k1_launch_ms": dyn_launch_ms, "k1_TFLOPs": k1,
+                          "k1_frac_burst": k1 / pk["tf_burst"], "job_TFLOPs": (fdyn + fact + fvvc) * tr_s / 1e12,
+                          "job_frac_burst": (fdyn + fact + fvvc) * tr_s / 1e12 / (pk["tf_burst"] * world),
+                          "writeout_GBps": rig.row_bytes() * tr_s / 1e9,
+                          "gae_GBps": 32.0 * B * H / (gae_launch_ms * 1e-3) / 1e9 if gae_launch_ms > 0 else None})
+            rig.torch.cuda.empty_cache()
+    if rig.rank != 0:
+        return
+    best = max(cells, key=lambda c: c["transitions_per_s"])
+    big = cells[-1]
+    line = base_line(rig, args, cfg, big["transitions_per_s"], big["ms_per_pass"], {
+        "value_is": "the largest cell (H=%d, B_total=%d)" % (big["H"], big["B_total"]), "horizons": Hs, "batches_total": Bs,
+        "l2": "cells below ~50k start states per GPU fit the 126 MB L2; no explicit flush",
+        "flop_per_transition": fdyn + fact + fvvc})
+    line["roofline"] = {"bound": "tensor", "kernel": "dynamics-ensemble GEMM chain (K1), largest cell", "achieved": big["k1_TFLOPs"],
+                        "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": big["k1_frac_burst"], "frac_burst": big["k1_frac_burst"],
+                        "frac_sustained": big["k1_TFLOPs"] / pk["tf_sus"], "traffic": None}
+    line["cells"] = cells
+    line["best_cell"] = best
+    line["cpu_baseline"] = None
+    line["e2e"] = None
+    line["gpu_launches"] = int(launches_total)
+    line["clocks"] = clk
+    emit(line)
 
 
 L_PROF_DYN, L_PROF_GAE = 0, 1
@@ -503,6 +818,14 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--batch", type=int, default=100000, help="start states per GPU")
     ap.add_argument("--cpu-batch", type=int, default=500, help="start states of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end legs (e2e = null)")
+    ap.add_argument("--config", default="hcs", choices=sorted(CONFIGS), help="BASELINE.json configs[1..4]; default configs[1]")
+    ap.add_argument("--mode", default="mean", choices=["mean", "injected"],
+                    help="transition mode: deterministic mean (reference behaviour) or mean + std*eps")
+    ap.add_argument("--fuse", action="store_true", help="use the fused rollout step (CMBPO_ROLLOUT_FUSE)")
+    ap.add_argument("--total", type=int, default=0, help="ant1m: total start states (default 1,000,000)")
+    ap.add_argument("--sweep-h", default="1,2,5,10,20,30")
+    ap.add_argument("--sweep-b", default="10000,100000,1000000,4000000")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print at C level while the job runs
     # (NCCL's version banner) goes to stderr; the real stdout is restored for the final print

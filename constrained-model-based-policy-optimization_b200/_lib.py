@@ -85,6 +85,8 @@ SIGNATURES = {
     "cmbpo_adv_stats_pass1": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
     "cmbpo_adv_stats_pass2": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _f, _vp]),
     "cmbpo_adv_normalise": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _vp, _f, _f, _f]),
+    "cmbpo_adv_stats_pass2_dev": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _vp, _vp]),
+    "cmbpo_adv_normalise_dev": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
     "cmbpo_path_offsets": (_i, [_vp, _vp, _i64, _vp]),
     "cmbpo_compact_field": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "cmbpo_scatter_rows": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _i64]),

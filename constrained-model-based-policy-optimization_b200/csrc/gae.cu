@@ -42,15 +42,32 @@ __global__ void gae_paths_strict_kernel(const float* __restrict__ rew, const flo
     double y = 0.0, cy = 0.0;
     float vn = last_val[p], cvn = last_cval[p];
     const int64_t base = p * ps;
-#pragma unroll 4
-    for (int t = len - 1; t >= 0; --t) {
-        int64_t i = base + (int64_t)t * ts;
-        float r = rew[i], v = val[i], c = cost[i], cv = cval[i];
-        float a, rt, ca, crt;
-        gae_step(r, v, vn, k.g32, k.d, y, a, rt);
-        gae_step(c, cv, cvn, k.cg32, k.cd, cy, ca, crt);
-        adv[i] = a; ret[i] = rt; cadv[i] = ca; cret[i] = crt;
-        vn = v; cvn = cv;
+    // The recurrence is sequential, the loads are not: the inputs of GB consecutive steps (4 x GB independent,
+    // warp-coalesced loads) are fetched before the first of them is consumed.  One thread per path gives only
+    // ~30 % occupancy at 100 k paths, so the bytes in flight have to come from each thread.
+    constexpr int GB = 16;
+    for (int t0 = len - 1; t0 >= 0; t0 -= GB) {
+        float r[GB], v[GB], c[GB], cv[GB];
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+            const int t = t0 - j;
+            if (t >= 0) {
+                const int64_t i = base + (int64_t)t * ts;
+                r[j] = __ldg(rew + i); v[j] = __ldg(val + i); c[j] = __ldg(cost + i); cv[j] = __ldg(cval + i);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+            const int t = t0 - j;
+            if (t >= 0) {
+                const int64_t i = base + (int64_t)t * ts;
+                float a, rt, ca, crt;
+                gae_step(r[j], v[j], vn, k.g32, k.d, y, a, rt);
+                gae_step(c[j], cv[j], cvn, k.cg32, k.cd, cy, ca, crt);
+                adv[i] = a; ret[i] = rt; cadv[i] = ca; cret[i] = crt;
+                vn = v[j]; cvn = cv[j];
+            }
+        }
     }
 }
 
@@ -255,9 +272,11 @@ __global__ void stats_pass1_kernel(const float* __restrict__ adv, const float* _
 
 __global__ void stats_pass2_kernel(const float* __restrict__ adv, int64_t n_paths, int max_len,
                                    int64_t ps, int64_t ts, const int32_t* __restrict__ length,
-                                   float mean, double* __restrict__ partial) {
+                                   float mean, const double* __restrict__ sums_dev, double* __restrict__ partial) {
     __shared__ double sh[32];
     double ss = 0;
+    // device-resident statistics (no host round trip): mean = float32(sum) / float32(n) as mpi_tools.py:82-83
+    if (sums_dev) mean = (sums_dev[0] > 0.0) ? __fdiv_rn((float)sums_dev[1], (float)sums_dev[0]) : 0.f;
     const int64_t total = n_paths * (int64_t)max_len;
     const bool path_fast = ps <= ts;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -296,7 +315,14 @@ __global__ void __launch_bounds__(256) stats_final_kernel(const double* __restri
 __global__ void normalise_kernel(float* __restrict__ adv, float* __restrict__ cadv, int64_t n_paths,
                                  int max_len, int64_t ps, int64_t ts,
                                  const int32_t* __restrict__ length, float mean, float denom,
-                                 float cmean) {
+                                 float cmean, const double* __restrict__ sums_dev) {
+    if (sums_dev) {                     // sums = (n, sum adv, sum cadv, sum ret, sum cret, sum (adv-mean)^2), all-reduced
+        if (!(sums_dev[0] > 0.0)) return;
+        const float n = (float)sums_dev[0];
+        mean = __fdiv_rn((float)sums_dev[1], n);
+        cmean = __fdiv_rn((float)sums_dev[2], n);
+        denom = __fadd_rn(__fsqrt_rn(__fdiv_rn((float)sums_dev[5], n)), 1e-8f);     // mpi_tools.py:85-86, modelbuffer.py:199
+    }
     const int64_t total = n_paths * (int64_t)max_len;
     const bool path_fast = ps <= ts;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -426,7 +452,7 @@ extern "C" int cmbpo_gae_paths(cmbpo_ctx* ctx, const float* rew, const float* va
             rew, val, cost, cval, n_paths, max_len, length, last_val, last_cval, k, adv, ret, cadv,
             cret);
     } else {
-        int threads = 128;
+        int threads = 64;           // small blocks: ~10 per SM at 100 k paths, a smooth tail
         int64_t blocks = (n_paths + threads - 1) / threads;
         gae_paths_strict_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
             rew, val, cost, cval, n_paths, max_len, path_stride, time_stride, length, last_val,
@@ -489,9 +515,38 @@ extern "C" int cmbpo_adv_stats_pass2(cmbpo_ctx* ctx, const float* adv, int64_t n
     double* partial;
     if (cmbpo_ws_get(ctx, 7, (size_t)blocks * 8 * sizeof(double), (void**)&partial)) return 1;
     stats_pass2_kernel<<<blocks, threads, 0, ctx->stream>>>(adv, n_paths, max_len, path_stride,
-                                                          time_stride, length, adv_mean, partial);
+                                                          time_stride, length, adv_mean, nullptr, partial);
     stats_final_kernel<<<1, 256, 0, ctx->stream>>>(partial, blocks, 1, 1, sums_out, 5);
     ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cmbpo_adv_stats_pass2_dev(cmbpo_ctx* ctx, const float* adv, int64_t n_paths, int max_len,
+                                         int64_t path_stride, int64_t time_stride, const int32_t* length,
+                                         const double* sums_dev, double* sums_out) {
+    CMBPO_CHECK(ctx && sums_dev && sums_out, "null argument");
+    int threads = 256;
+    int blocks = grid_for(ctx, n_paths * (int64_t)max_len, threads);
+    double* partial;
+    if (cmbpo_ws_get(ctx, 7, (size_t)blocks * 8 * sizeof(double), (void**)&partial)) return 1;
+    stats_pass2_kernel<<<blocks, threads, 0, ctx->stream>>>(adv, n_paths, max_len, path_stride,
+                                                          time_stride, length, 0.f, sums_dev, partial);
+    stats_final_kernel<<<1, 256, 0, ctx->stream>>>(partial, blocks, 1, 1, sums_out, 5);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cmbpo_adv_normalise_dev(cmbpo_ctx* ctx, float* adv, float* cadv, int64_t n_paths,
+                                       int max_len, int64_t path_stride, int64_t time_stride,
+                                       const int32_t* length, const double* sums_dev) {
+    CMBPO_CHECK(ctx && sums_dev, "null argument");
+    int threads = 256;
+    int blocks = grid_for(ctx, n_paths * (int64_t)max_len, threads);
+    normalise_kernel<<<blocks, threads, 0, ctx->stream>>>(adv, cadv, n_paths, max_len, path_stride,
+                                                         time_stride, length, 0.f, 1.f, 0.f, sums_dev);
+    ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -506,7 +561,7 @@ extern "C" int cmbpo_adv_normalise(cmbpo_ctx* ctx, float* adv, float* cadv, int6
     float denom = adv_std + 1e-8f;   // float32(std) + EPS, modelbuffer.py:199
     normalise_kernel<<<blocks, threads, 0, ctx->stream>>>(adv, cadv, n_paths, max_len, path_stride,
                                                          time_stride, length, adv_mean, denom,
-                                                         cadv_mean);
+                                                         cadv_mean, nullptr);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -271,6 +271,35 @@ class Engine:
         st["adv_std"] = np.float32(combine_pass2(ssq, st["n"]))
         return st
 
+    def adv_statistics_device(self, adv, cadv, ret, cret, n_paths, max_len, path_stride, time_stride,
+                              length, reduce_fn=None):
+        """The same two passes with the sums kept on the device: no host synchronisation, so the host can queue
+        the normalisation and whatever follows without waiting for the scans; with N > 1 the ranks meet only in the
+        two all-reduces.  Returns the device tensor of 8 float64 sums (see `stats_from_sums`)."""
+        t = self.torch
+        sums = self.zeros(8, dtype=t.float64)
+        L.check(self.lib.cmbpo_adv_stats_pass1(self.h, self._p(adv), self._p(cadv), self._p(ret),
+                                               self._p(cret), n_paths, max_len, path_stride,
+                                               time_stride, self._p(length), self._p(sums)))
+        if reduce_fn is not None:
+            reduce_fn(sums)
+        L.check(self.lib.cmbpo_adv_stats_pass2_dev(self.h, self._p(adv), n_paths, max_len, path_stride,
+                                                   time_stride, self._p(length), self._p(sums), self._p(sums)))
+        if reduce_fn is not None:
+            reduce_fn(sums[5:6])                 # in place: a one-element view of the same memory
+        return sums
+
+    def adv_normalise_device(self, adv, cadv, n_paths, max_len, path_stride, time_stride, length, sums):
+        L.check(self.lib.cmbpo_adv_normalise_dev(self.h, self._p(adv), self._p(cadv), n_paths, max_len,
+                                                 path_stride, time_stride, self._p(length), self._p(sums)))
+
+    @staticmethod
+    def stats_from_sums(s):
+        """dict of adv_statistics() from a HOST copy of the 8 sums of adv_statistics_device()."""
+        st = combine_pass1(s)
+        st["adv_std"] = np.float32(combine_pass2(float(s[5]), st["n"])) if st["n"] else np.float32(0)
+        return st
+
     def adv_normalise(self, adv, cadv, n_paths, max_len, path_stride, time_stride, length, st):
         L.check(self.lib.cmbpo_adv_normalise(self.h, self._p(adv), self._p(cadv), n_paths, max_len,
                                              path_stride, time_stride, self._p(length),

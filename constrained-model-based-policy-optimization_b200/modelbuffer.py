@@ -166,11 +166,13 @@ class ModelBuffer:
         B, T = self.batch_size, self.max_path_length
         if not self._device_lengths:
             b.length.copy_(e.to_device(self._length, t.int32))
-        st = e.adv_statistics(b.adv, b.cadv, b.ret, b.cret, B, T, 1, B, b.length, self.reduce_fn)
-        if st["n"] > 0:
-            e.adv_normalise(b.adv, b.cadv, B, T, 1, B, b.length, st)
+        # statistics and normalisation are queued without a host round trip (device-resident sums); the first
+        # synchronisation is the row count below, by which time everything is in flight
+        sums = e.adv_statistics_device(b.adv, b.cadv, b.ret, b.cret, B, T, 1, B, b.length, self.reduce_fn)
+        e.adv_normalise_device(b.adv, b.cadv, B, T, 1, B, b.length, sums)
         off = e.path_offsets(b.length)
         n_rows = int(off[-1].item())
+        st = e.stats_from_sums(sums.cpu().numpy())
         O, A = self.obs_dim, self.act_dim
         def tgt(i, width, vector):
             return None if staging_gen is None else self._staging(staging_gen, i, n_rows, width, vector)

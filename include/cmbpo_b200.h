@@ -304,6 +304,19 @@ int cmbpo_adv_stats_pass2(cmbpo_ctx* ctx, const float* adv, int64_t n_paths, int
 int cmbpo_adv_normalise(cmbpo_ctx* ctx, float* adv, float* cadv, int64_t n_paths, int max_len,
                         int64_t path_stride, int64_t time_stride, const int32_t* length,
                         float adv_mean, float adv_std, float cadv_mean);
+/*
+ * The same two steps with the statistics kept in DEVICE memory (no host round trip between the passes, so a
+ * multi-GPU job's ranks are only coupled by the two NCCL all-reduces, not by host synchronisations):
+ * sums_dev = the 8 doubles of pass 1 (all-reduced); pass2_dev forms mean = float32(sum)/float32(n) on the device
+ * (mpi_tools.py:82-83) and writes the local sum of squares to sums_out[5]; normalise_dev forms mean, cmean and
+ * std = sqrt(float32(sumsq)/float32(n)) from the (all-reduced) sums (mpi_tools.py:85-86).  n == 0: no-ops.
+ */
+int cmbpo_adv_stats_pass2_dev(cmbpo_ctx* ctx, const float* adv, int64_t n_paths, int max_len,
+                              int64_t path_stride, int64_t time_stride, const int32_t* length,
+                              const double* sums_dev, double* sums_out);
+int cmbpo_adv_normalise_dev(cmbpo_ctx* ctx, float* adv, float* cadv, int64_t n_paths, int max_len,
+                            int64_t path_stride, int64_t time_stride, const int32_t* length,
+                            const double* sums_dev);
 
 /*
  * ModelBuffer.get()'s `buf[populated_mask]` (modelbuffer.py:218): gathers the valid (p,t)

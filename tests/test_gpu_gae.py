@@ -130,6 +130,35 @@ def test_stats_normalise_compact(engine):
     assert np.array_equal(flat1, ret[mask])
 
 
+def test_device_resident_statistics_equal_host_path(engine):
+    """adv_statistics_device / adv_normalise_device (no host round trip) give bit-identical statistics and arrays
+    to the host-scalar entry points, including the empty batch."""
+    import torch
+    B, T = 913, 35
+    rng = np.random.default_rng(5)
+    length = rng.integers(0, T, B).astype(np.int32)
+    adv, cadv, ret, cret = (rng.standard_normal((B, T)).astype(np.float32) * 2 - 0.3 for _ in range(4))
+    tm = lambda a: engine.to_device(np.ascontiguousarray(np.swapaxes(a, 0, 1)))
+    d_len = engine.to_device(length, torch.int32)
+    a1, c1, r1, cr1 = tm(adv), tm(cadv), tm(ret), tm(cret)
+    a2, c2 = tm(adv), tm(cadv)
+    st = engine.adv_statistics(a1, c1, r1, cr1, B, T, 1, B, d_len)
+    engine.adv_normalise(a1, c1, B, T, 1, B, d_len, st)
+    sums = engine.adv_statistics_device(a2, c2, r1, cr1, B, T, 1, B, d_len)
+    engine.adv_normalise_device(a2, c2, B, T, 1, B, d_len, sums)
+    st2 = engine.stats_from_sums(sums.cpu().numpy())
+    for k in ("n", "adv_mean", "adv_std", "cadv_mean", "ret_mean", "cret_mean"):
+        assert st[k] == st2[k], k
+    assert torch.equal(a1, a2) and torch.equal(c1, c2)
+    # empty batch: nothing is touched, n == 0
+    zero = engine.to_device(np.zeros(B, np.int32), torch.int32)
+    a3 = tm(adv)
+    sums0 = engine.adv_statistics_device(a3, c2, r1, cr1, B, T, 1, B, zero)
+    engine.adv_normalise_device(a3, c2, B, T, 1, B, zero, sums0)
+    assert engine.stats_from_sums(sums0.cpu().numpy())["n"] == 0
+    assert np.array_equal(a3.cpu().numpy().T, adv)
+
+
 def test_path_offsets_large(engine):
     import torch
     rng = np.random.default_rng(1)
