@@ -46,6 +46,12 @@ class RolloutCfg(C.Structure):
 
 
 ROLLOUT_NO_COMPACT, ROLLOUT_FUSE, ROLLOUT_NO_STORE = 1, 2, 4
+LOSS_MSPE, LOSS_MSE = 0, 1
+
+
+class TrainCfg(C.Structure):
+    _fields_ = [("loss", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("weight_decay", C.c_float * 8), ("math", C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/cmbpo_b200.h declares
@@ -87,6 +93,13 @@ SIGNATURES = {
     "cmbpo_adv_normalise": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _vp, _f, _f, _f]),
     "cmbpo_adv_stats_pass2_dev": (_i, [_vp, _vp, _i64, _i, _i64, _i64, _vp, _vp, _vp]),
     "cmbpo_adv_normalise_dev": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _vp, _vp]),
+    "cmbpo_ens_train_begin": (_i, [_vp, _i]),
+    "cmbpo_ens_train_step": (_i, [_vp, _i, _vp, _vp, _i64, C.POINTER(TrainCfg), _vp]),
+    "cmbpo_ens_train_loss": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
+    "cmbpo_ens_train_grads": (_i, [_vp, _i, _i, _vp, _vp]),
+    "cmbpo_ens_train_end": (_i, [_vp, _i, _vp, _i]),
+    "cmbpo_net_get_weights": (_i, [_vp, _i, _i, _vp, _vp]),
+    "cmbpo_net_set_scalers": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "cmbpo_path_offsets": (_i, [_vp, _vp, _i64, _vp]),
     "cmbpo_compact_field": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "cmbpo_scatter_rows": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _i64]),

@@ -68,6 +68,7 @@ extern "C" int cmbpo_ctx_destroy(cmbpo_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (int w = 0; w < CMBPO_NET_COUNT; ++w) train_free(ctx, w);
     for (Net& n : ctx->nets) net_free(n);
     net_free(ctx->polnet);
     if (ctx->log_std) cudaFree(ctx->log_std);
@@ -150,6 +151,7 @@ extern "C" int cmbpo_net_set_weights(cmbpo_ctx* ctx, int which, int E, int n_lay
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     Net& n = ctx->nets[which];
+    train_free(ctx, which);                  // a new set of variables: the optimiser state goes with the old one
     net_free(n);
     n.E = E; n.n_layers = n_layers; n.probabilistic = probabilistic != 0;
     for (int l = 0; l <= n_layers; ++l) n.dims[l] = dims[l];

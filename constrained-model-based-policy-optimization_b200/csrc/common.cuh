@@ -54,6 +54,7 @@ struct Net {
     size_t tc_pack_bytes[3] = {0, 0, 0};
     float* tc_bias = nullptr;   // biases re-laid for the epilogue
     int tc_group = 1;           // members per tcgen05 work unit (4 for narrow ensembles)
+    int tc_hd = 0;              // hidden width padded to the kernel instantiation (128 / 256 / 512)
     int tc_fold = 0;            // layer-0 bias folded into the packed layer-0 tiles (input dim + 2 <= 64)
     // merged nets only: hidden activation per member (CMBPO_ACT_*); all -1 for an ordinary ensemble
     int member_act[CMBPO_MAX_E] = {-1, -1, -1, -1, -1, -1, -1, -1};
@@ -92,6 +93,8 @@ struct cmbpo_ctx {
     // rollout: page-locked mirror of the live row count + events (early exit once every path ended)
     int64_t* host_n = nullptr;      // [4]
     cudaEvent_t n_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // ensemble training (train.cu): optimiser state, activations and the cuBLAS handle per network slot
+    void* train[CMBPO_NET_COUNT] = {nullptr};
 };
 
 // grow-only scratch
@@ -134,6 +137,7 @@ bool ens_tc_supported(const Net& net);
 int ens_tc_prepare(cmbpo_ctx* ctx, Net& net);
 int policy_pack_build(cmbpo_ctx* ctx);
 void net_free(Net& n);
+void train_free(cmbpo_ctx* ctx, int which);
 // n_dev (tcgen05 precisions only): live row count in device memory, <= N; rows beyond it are skipped
 int ens_forward(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, bool x_is_3d, float* out_raw,
                 int precision, const int64_t* n_dev = nullptr);

@@ -883,6 +883,7 @@ template <int FMT>
 __global__ void pack_weights_kernel(const float* W0, const float* W1, const float* W2, const float* b0, int K0, int HD,
                                     int Nout, int E, int group, const Stage* stages, int n_stages,
                                     unsigned long long member_bytes, PackCfg cfg, uint8_t* out) {
+    // HD = the REAL hidden width of the fp32 master copy; tiles beyond it (the instantiation's padded width) are zeros
     const Stage st = stages[blockIdx.x];
     const int e = blockIdx.y * group + st.member;        // real member (may be >= E in the last group: zeros)
     const float* W; int K, M;
@@ -908,18 +909,19 @@ __global__ void pack_weights_kernel(const float* W0, const float* W1, const floa
 
 // per unit: [b0 of the G members | b1 of the G members | b2 (NP each) of the G members]; HD = member width.
 // The hidden biases of swish members are halved like their weights.
-__global__ void pack_bias_kernel(const float* b0, const float* b1, const float* b2, int HD, int Nout, int NP,
+__global__ void pack_bias_kernel(const float* b0, const float* b1, const float* b2, int HD, int HR, int Nout, int NP,
                                  int E, int group, PackCfg cfg, float* out) {
+    // HD = padded member width (layout), HR = real width of the master copy
     const int u = blockIdx.x;
     const int stride = group * (2 * HD + NP);
     for (int i = threadIdx.x; i < stride; i += blockDim.x) {
         float v = 0.f;
         if (i < group * HD) {
             const int e = u * group + i / HD;
-            if (e < E) v = b0[(size_t)e * HD + i % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
+            if (e < E && i % HD < HR) v = b0[(size_t)e * HR + i % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
         } else if (i < 2 * group * HD) {
             const int k = i - group * HD, e = u * group + k / HD;
-            if (e < E) v = b1[(size_t)e * HD + k % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
+            if (e < E && k % HD < HR) v = b1[(size_t)e * HR + k % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
         } else {
             const int k = i - 2 * group * HD, e = u * group + k / NP, c = k % NP;
             if (e < E && c < Nout) v = b2[(size_t)e * Nout + c];
@@ -927,6 +929,10 @@ __global__ void pack_bias_kernel(const float* b0, const float* b1, const float* 
         out[(size_t)u * stride + i] = v;
     }
 }
+
+// hidden width padded to a kernel instantiation (zero weights / biases: swish(0) = tanh(0) = 0, so the padded neurons
+// contribute nothing to the next layer)
+int padded_hd(int h) { return h <= 128 ? 128 : (h <= 256 ? 256 : 512); }
 
 struct OutShape { int NP, parts; };
 OutShape out_shape(int Nout) {
@@ -1015,7 +1021,7 @@ int launch_tc_hd(cmbpo_ctx* ctx, const TcParams& p, int hd, int act) {
 bool ens_tc_supported(const Net& n) {
     if (!n.loaded || n.n_layers != 3) return false;
     const int hd = n.dims[1];
-    if (n.dims[2] != hd || (hd != 128 && hd != 256 && hd != 512)) return false;
+    if (n.dims[2] != hd || hd < 1 || hd > 512) return false;      // any width <= 512 (padded to 128 / 256 / 512)
     if (n.dims[0] > 64 || n.dims[3] > 128) return false;
     if (n.acts[0] != n.acts[1] || n.acts[2] != CMBPO_ACT_NONE) return false;
     return n.acts[0] == CMBPO_ACT_SWISH || n.acts[0] == CMBPO_ACT_TANH;
@@ -1023,7 +1029,8 @@ bool ens_tc_supported(const Net& n) {
 
 // pack both 16-bit formats once per weight upload: [main stream | W2 stream] per precision
 int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
-    const int HD = net.dims[1], K0 = net.dims[0], Nout = net.dims[3];
+    const int HR = net.dims[1], HD = padded_hd(HR), K0 = net.dims[0], Nout = net.dims[3];
+    net.tc_hd = HD;
     const OutShape os = out_shape(Nout);
     // narrow ensembles run grouped: 4 members of width 128 per unit (their OUT blocks share 64 columns)
     const int group = (HD == 128 && net.E >= 2 && os.NP <= 16) ? 4 : 1;
@@ -1049,15 +1056,15 @@ int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
         uint8_t* base2 = base + (size_t)n_units * main_bytes;
         dim3 g1((unsigned)mp.size(), n_units), g2((unsigned)wp.size(), n_units);
         if (prec == CMBPO_PREC_FP16) {
-            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HD, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
-            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HD, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
+            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HR, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
+            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HR, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
         } else {
-            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HD, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
-            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HD, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
+            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HR, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
+            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HR, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
         }
     }
     CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)n_units * group * (2 * HD + os.NP) * sizeof(float)));
-    pack_bias_kernel<<<n_units, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, Nout, os.NP, net.E, group, pc, net.tc_bias);
+    pack_bias_kernel<<<n_units, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, HR, Nout, os.NP, net.E, group, pc, net.tc_bias);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaFree(d_mp));
     CUDA_TRY(cudaFree(d_wp));
@@ -1089,7 +1096,7 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     CMBPO_CHECK(net.tc_pack[precision], "tcgen05 weights not packed");
     if (N <= 0) return 0;
     CMBPO_CHECK((N + 127) / 128 * (int64_t)net.E < (int64_t)1 << 31, "too many rows for one launch");
-    const int HD = net.dims[1];
+    const int HD = net.tc_hd;                   // padded hidden width = kernel instantiation
     const OutShape os = out_shape(net.dims[3]);
     TcParams p;
     p.Nout = net.dims[3];

@@ -45,7 +45,7 @@ __global__ void gae_paths_strict_kernel(const float* __restrict__ rew, const flo
     // The recurrence is sequential, the loads are not: the inputs of GB consecutive steps (4 x GB independent,
     // warp-coalesced loads) are fetched before the first of them is consumed.  One thread per path gives only
     // ~30 % occupancy at 100 k paths, so the bytes in flight have to come from each thread.
-    constexpr int GB = 16;
+    constexpr int GB = 8;      // measured: 8 loads x 4 arrays in flight per thread; 16 (and 64-thread blocks) was slower
     for (int t0 = len - 1; t0 >= 0; t0 -= GB) {
         float r[GB], v[GB], c[GB], cv[GB];
 #pragma unroll
@@ -452,7 +452,7 @@ extern "C" int cmbpo_gae_paths(cmbpo_ctx* ctx, const float* rew, const float* va
             rew, val, cost, cval, n_paths, max_len, length, last_val, last_cval, k, adv, ret, cadv,
             cret);
     } else {
-        int threads = 64;           // small blocks: ~10 per SM at 100 k paths, a smooth tail
+        int threads = 128;
         int64_t blocks = (n_paths + threads - 1) / threads;
         gae_paths_strict_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
             rew, val, cost, cval, n_paths, max_len, path_stride, time_stride, length, last_val,

@@ -130,6 +130,54 @@ class Engine:
         self.nets[which] = dict(E=E, dims=dims, D=last // 2 if probabilistic else last,
                                 probabilistic=bool(probabilistic), elite_inds=elite)
 
+    # ------------------------------------------------------------------ ensemble training
+    def train_begin(self, which):
+        L.check(self.lib.cmbpo_ens_train_begin(self.h, which))
+
+    def train_step(self, which, x, y, cfg, loss_out=None):
+        """One Adam step of slot `which` on x [E,bs,in], y [E,bs,D] (device tensors, member e on slice e)."""
+        t = self.torch
+        x = self.to_device(x, t.float32)
+        y = self.to_device(y, t.float32)
+        assert x.dim() == 3 and y.dim() == 3 and x.shape[:2] == y.shape[:2]
+        L.check(self.lib.cmbpo_ens_train_step(self.h, which, self._p(x), self._p(y), int(x.shape[1]), C.byref(cfg),
+                                              self._p(loss_out)))
+
+    def train_loss(self, which, x, y):
+        """`self.loss` of the reference (pe.py:264): [E] device tensor of mean 0.5 (mean - transform(y))^2."""
+        t = self.torch
+        x = self.to_device(x, t.float32)
+        y = self.to_device(y, t.float32)
+        out = self.empty(int(x.shape[0]))
+        L.check(self.lib.cmbpo_ens_train_loss(self.h, which, self._p(x), self._p(y), int(x.shape[1]), self._p(out)))
+        return out
+
+    def train_grads(self, which, layer):
+        m = self.nets[which]
+        dW = self.empty(m["E"], m["dims"][layer], m["dims"][layer + 1])
+        db = self.empty(m["E"], m["dims"][layer + 1])
+        L.check(self.lib.cmbpo_ens_train_grads(self.h, which, layer, self._p(dW), self._p(db)))
+        return dW, db
+
+    def get_weights(self, which, layer):
+        m = self.nets[which]
+        W = self.empty(m["E"], m["dims"][layer], m["dims"][layer + 1])
+        b = self.empty(m["E"], m["dims"][layer + 1])
+        L.check(self.lib.cmbpo_net_get_weights(self.h, which, layer, self._p(W), self._p(b)))
+        return W, b
+
+    def set_scalers(self, which, mu_in=None, var_in=None, mu_out=None, var_out=None):
+        keep = [None if a is None else _as_f32(np.asarray(a).reshape(-1)) for a in (mu_in, var_in, mu_out, var_out)]
+        p = [C.c_void_p(None if a is None else a.ctypes.data) for a in keep]
+        L.check(self.lib.cmbpo_net_set_scalers(self.h, which, *p))
+
+    def train_end(self, which, elite_inds=None):
+        el = None if elite_inds is None else [int(i) for i in elite_inds]
+        arr = (C.c_int * max(1, len(el or [])))(*(el or [0]))
+        L.check(self.lib.cmbpo_ens_train_end(self.h, which, arr if el else None, len(el or [])))
+        if el:
+            self.nets[which]["elite_inds"] = el
+
     def set_actor(self, W, b, log_std):
         """W[l]: [in,out] dense kernels, tanh hidden, linear output (ac_network.py:26-33)."""
         t = self.torch

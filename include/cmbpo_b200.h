@@ -319,6 +319,41 @@ int cmbpo_adv_normalise_dev(cmbpo_ctx* ctx, float* adv, float* cadv, int64_t n_p
                             const double* sums_dev);
 
 /*
+ * the ensemble training step -- the body of the batch loop of PE.train (models/pens/pe.py:547-567).
+ *   train_begin  allocates the optimiser state of slot `which` (Adam moments, zero; step counter 0).  The state
+ *                persists across calls like tf.train.AdamOptimizer's variables; cmbpo_net_set_weights drops it.
+ *   train_step   x [E,bs,in], y [E,bs,D] (device): member e trains on ITS OWN batch (bootstrap rows, pe.py:523,549).
+ *                Forward (fc.py:74-95), loss, backward, Adam update of the fp32 master weights in place.
+ *                loss = CMBPO_LOSS_MSPE (probabilistic nets; pe.py:921-973) or CMBPO_LOSS_MSE (pe.py:840-919 with
+ *                inc_var_loss=False); weight_decay[l] multiplies tf.nn.l2_loss(W_l) (fc.py:168-169;
+ *                pe_factory.py:50-55: decay/4, decay/2 ..., decay).  loss_out (device, [E], may be NULL): the
+ *                per-member loss vector the reference's loss function returns (before decay).
+ *                math: 0 = fp32 GEMMs, 1 = TF32 tensor-core GEMMs (cuBLAS).
+ *   train_loss   `self.loss` of the reference (pe.py:264): mean 0.5 (mean - transform(y))^2 per member, no update.
+ *   train_grads  device copies of the last step's gradients of one layer (before decay): dW [E,in,out], db [E,out].
+ *   train_end    installs new elites (NULL keeps them) and re-packs the tcgen05 weight streams: predictions and
+ *                rollouts after it see the trained weights (pe.py:396-399, 601-607).
+ *   cmbpo_net_get_weights / cmbpo_net_set_scalers: device copies of one layer's variables; new scaler statistics
+ *                (TensorStandardScaler.fit, pens/utils.py:119-138; host pointers).
+ */
+enum { CMBPO_LOSS_MSPE = 0, CMBPO_LOSS_MSE = 1 };
+typedef struct {
+    int loss;
+    float lr, beta1, beta2, eps;       /* tf.train.AdamOptimizer: 1e-3 (cmbpo.py:51), 0.9, 0.999, 1e-8 */
+    float weight_decay[8];
+    int math;
+} cmbpo_train_cfg;
+int cmbpo_ens_train_begin(cmbpo_ctx* ctx, int which);
+int cmbpo_ens_train_step(cmbpo_ctx* ctx, int which, const float* x, const float* y, int64_t bs,
+                         const cmbpo_train_cfg* cfg, float* loss_out);
+int cmbpo_ens_train_loss(cmbpo_ctx* ctx, int which, const float* x, const float* y, int64_t bs, float* loss_out);
+int cmbpo_ens_train_grads(cmbpo_ctx* ctx, int which, int layer, float* dW, float* db);
+int cmbpo_ens_train_end(cmbpo_ctx* ctx, int which, const int* elite_inds, int n_elite);
+int cmbpo_net_get_weights(cmbpo_ctx* ctx, int which, int layer, float* W, float* b);
+int cmbpo_net_set_scalers(cmbpo_ctx* ctx, int which, const float* mu_in, const float* var_in,
+                          const float* mu_out, const float* var_out);
+
+/*
  * ModelBuffer.get()'s `buf[populated_mask]` (modelbuffer.py:218): gathers the valid (p,t)
  * entries of a time-major field [T,B,width] into out[row,width], rows ordered path-major then
  * time (numpy boolean-mask order).  row_offsets [B+1] = exclusive prefix sum of length
