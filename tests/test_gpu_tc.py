@@ -104,6 +104,49 @@ def test_rollout_tc_other_ensemble_shapes(engine, num_nets, hidden, B):
         assert np.allclose(da[m, t], db[m, t], rtol=5e-2, atol=1e-4), t      # closed-form vs all-pairs KL, fp16 inputs
 
 
+@pytest.mark.parametrize("key,O,hidden,B", [("hcs", 17, (200, 200), 500), ("hcs", 20, (512, 512), 300),
+                                            ("ant", 29, (300, 300), 257), ("hcs", 20, (64, 64), 100),
+                                            ("hum", 47, (200, 200), 130)])
+def test_rollout_tc_padded_widths_and_real_hcs_obs(engine, key, O, hidden, B):
+    """Hidden widths that are not a kernel instantiation (200, 300, 64: zero padded to 256 / 512 / 128 at pack
+    time) and the O = 20 observation of the real HalfCheetahSafe environment (the kernels must
+    be generic in O / A): single-step prediction against the oracle within the tolerance of test_predict_ensemble_tc,
+    and a short rollout against the fp32 CUDA-core path."""
+    import cmbpo_b200 as cb
+    task, _, A = TASKS[key]
+    T = 6
+    dyn, actor, v, vc = orc.make_problem(61, O, A, hidden=hidden, task=task)
+    obs, act = orc.make_states(62, B, O, A, dyn)
+    model, policy = load_problem(engine, dyn, actor, v, vc)
+    x = np.concatenate([obs, act], axis=1)
+    want_m, want_v = orc.pe_forward(dyn, x)
+    got_m, got_v = (t.cpu().numpy() for t in model.predict_ensemble_device(x, precision="fp16"))
+    sig = np.maximum(np.sqrt(dyn.var_out), 1e-2)
+    assert _err(got_m, want_m, sig) <= 1.0
+    assert float(np.max(np.abs(got_v - want_v) / want_v)) <= 1.5e-3
+    noise = orc.TableNoise(63, T, B, A, len(dyn.elite_inds))
+    env = cb.FakeEnv(ShapeEnv(O, A), task, model, True, True, False)
+    res = {}
+    for prec in ("fp32", "fp16"):
+        bufs = cb.RolloutBuffers(engine, B, T, O, A)
+        bufs.set_inputs(obs, noise.act_eps, noise.elite_pos)
+        bufs.run(env.env_cfg(True), precision=prec)
+        engine.synchronize()
+        res[prec] = bufs
+    a, b = res["fp32"], res["fp16"]
+    la, lb = a.length.cpu().numpy(), b.length.cpu().numpy()
+    assert (la != lb).mean() <= 0.02 + 1.0 / B
+    same = la == lb
+    scale = np.maximum(np.sqrt(dyn.var_in[0, :O]), 1e-2)
+    na, nb = a.host("nextobs"), b.host("nextobs")
+    va, vb = a.host("val"), b.host("val")
+    for t in range(T - 1):
+        m = same & (la > t)
+        if m.any():
+            assert np.max(np.abs(na[m, t] - nb[m, t]) / scale) <= 3e-3 * (t + 1), t
+            assert np.allclose(va[m, t], vb[m, t], rtol=2e-2, atol=2e-2), t
+
+
 @pytest.mark.parametrize("E,N", [(2, 20000), (5, 5000), (5, 20000)])
 def test_width256_two_part_output_many_units(engine, E, N):
     """Regression: 256-wide nets with a two-part output (> 64 columns, single-buffered H2) and several
