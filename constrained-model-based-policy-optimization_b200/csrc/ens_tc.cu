@@ -323,9 +323,17 @@ __device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, const f
 // belongs to member j / (NC/G), uses only that member's K panels and accumulates into that member's
 // OUT block).  A narrow net processed alone is a serial chain of tiny MMAs and drains; grouped, the
 // chunks of G members flow through the same double-buffered pipeline as one wide member.
-template <int HD, int FMT, int ACT, bool DBG, int G, bool FUSE>
+// NMID > 0: DEEPER networks (2 + NMID hidden layers, e.g. the reference's code default (200,200,200,200),
+// algorithms/cmbpo.py:54): a second hidden-activation buffer HB in tensor memory, the hidden layers ping-pong
+// between H1 and HB (layer 0 writes H1; middle layer i reads buffer (i-1)&1 and writes buffer i&1; the last
+// hidden layer reads buffer NMID&1 and feeds H2 / layer 2 as before).  Needs 2 x HD/2 + 192 + NP <= 512 columns:
+// padded width <= 256 and NP <= 64.  No extra barriers: the tensor pipe executes in order, so by the time a
+// chunk's accumulator is handed to the epilogue every MMA that read the buffer it is about to overwrite has
+// finished; H1_FULL simply completes once per hidden layer instead of once per unit.
+template <int HD, int FMT, int ACT, bool DBG, int G, bool FUSE, int NMID = 0>
 __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams p) {
     static_assert(!FUSE || (G == 1 && !DBG), "the fused step kernel exists for ordinary (ungrouped) ensembles");
+    static_assert(NMID == 0 || (HD <= 256 && G == 1 && !FUSE && !DBG), "deep variant: width <= 256, ungrouped");
     constexpr int W2S = FUSE ? W2SLOT_F : W2SLOT;          // layer-2 ring slot bytes
     constexpr int NC = HD / 64;                     // 64-column chunks of a hidden layer
     constexpr int KP = HD / 64 / G;                 // 64-wide K panels of layer 1 (per member)
@@ -333,6 +341,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     constexpr int TPS = KP < 4 ? KP : 4;            // layer-1 tiles (K panels) per main-ring stage
     constexpr int G0 = NC < 4 ? NC : 4;             // layer-0 chunk tiles per main-ring stage
     constexpr uint32_t COL_H1 = 0, COL_D = HD / 2, COL_H2 = COL_D + 128;
+    constexpr uint32_t COL_HB = COL_H2 + 64;       // second hidden-activation buffer (NMID > 0 only)
+    constexpr int NHID = 1 + NMID;                 // HD x HD layers: NMID middle ones + the last hidden layer
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sXA = smem;
@@ -417,8 +427,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     if (++s == NSM) { s = 0; ph ^= 1; }
                 };
                 for (int j0 = 0; j0 < NC; j0 += G0) push(G0 * TILE);
-                for (int j = 0; j < NC; ++j)
-                    for (int kq = 0; kq < KP / TPS; ++kq) push(TPS * TILE);
+                for (int lyr = 0; lyr < NHID; ++lyr)
+                    for (int j = 0; j < NC; ++j)
+                        for (int kq = 0; kq < KP / TPS; ++kq) push(TPS * TILE);
             }
         }
         if (DBG && p.dbg && lane == 0) {
@@ -435,8 +446,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 {   // hidden-layer biases [b0 | b1] of this unit -> bias buffer (mb & 1)
                     wait_t<false>(bar + B_EMPTY + (mb & 1), ((mb >> 1) & 1) ^ 1, dummy);
                     if (elect_one()) {
-                        mbar_expect_tx(bar + B_FULL + (mb & 1), 2 * HD * 4);
-                        bulk_g2s(sBias + (mb & 1) * (BIAS_SLOT / 4), p.bias + (long long)e * p.bias_stride, 2 * HD * 4,
+                        mbar_expect_tx(bar + B_FULL + (mb & 1), (1 + NHID) * HD * 4);
+                        bulk_g2s(sBias + (mb & 1) * (BIAS_SLOT / 4), p.bias + (long long)e * p.bias_stride, (1 + NHID) * HD * 4,
                                  bar + B_FULL + (mb & 1));
                     }
                     __syncwarp();
@@ -547,7 +558,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     }
                     next_stage();
                 }
-                wait_t<DBG>(bar + H1_FULL, m & 1, c_h1);
+                for (int lyr = 0; lyr < NHID; ++lyr) {      // the HD x HD layers: middle ones (deep nets), then the last hidden
+                const uint32_t col_a = (NMID > 0 && (lyr & 1)) ? COL_HB : COL_H1;     // A operand: the buffer the layer before wrote
+                wait_t<DBG>(bar + H1_FULL, (m * NHID + lyr) & 1, c_h1);
                 tc_fence_after();
                 TRACE(0, 200);
                 // layer 1.  The accumulator hand-off of chunk j+1 is waited for BEFORE the last stage of chunk j
@@ -576,7 +589,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                         }
                         if (SINGLE || elect_one()) {
                             // TPS tiles x 4 K-steps from one asm statement (addresses chained inside, see tc_common.cuh)
-                            mma_f16_ts_tiles<TPS>(tmem + COL_D + buf * 64, tmem_rt + COL_H1 + ((j / CPM) * KP + kq * TPS) * 32,
+                            mma_f16_ts_tiles<TPS>(tmem + COL_D + buf * 64, tmem_rt + col_a + ((j / CPM) * KP + kq * TPS) * 32,
                                                   dW0 + (uint64_t)((s * STAGE) >> 4), idesc_h, kq > 0);
                             mma_commit(bar + W_EMPTY + s);
                             if (kq == KP / TPS - 1) mma_commit(bar + D_FULL + buf);
@@ -587,6 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     ++g;
                     TRACE(0, 400 + j);
                 }
+                }   // hidden-layer loop
                 ++m;
             }
         }
@@ -653,7 +667,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 // the tile's E-th member runs the row math for the tile
                 const FusedStep& f = p.fz;
                 if (mine) {
-                    const float* b2 = p.bias + (long long)prev_e * p.bias_stride + 2 * HD;
+                    const float* b2 = p.bias + (long long)prev_e * p.bias_stride + (1 + NHID) * HD;
                     float* dst = f.raw_tiles + ((size_t)prev_tile * p.E + prev_e) * p.Nout * 128 + row;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -678,7 +692,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             if (mine && prev_grow < n_rows) {
                 const int cb = (G > 1) ? 0 : c_begin;          // first output column of this warpgroup's slice
                 float* orow = p.out + (long long)(prev_e * G + (G > 1 ? wg : 0)) * p.out_member_stride + prev_grow * p.Nout;
-                const float* b2 = p.bias + (long long)prev_e * p.bias_stride + 2 * HD + (G > 1 ? wg * p.NP : 0);
+                const float* b2 = p.bias + (long long)prev_e * p.bias_stride + (1 + NHID) * HD + (G > 1 ? wg * p.NP : 0);
                 if ((p.Nout & 3) == 0) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -808,7 +822,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 // drains: the accumulator is not touched again before this member's first layer-2
                 // MMA, so the global stores stay off the MMA warp's critical path.
                 if (have_prev) out_epilogue();
-                for (int i = 0; i < NC / 2; ++i) {               // layer-1 chunk j -> an H2 buffer
+                if (NMID > 0) {
+                    for (int lyr = 1; lyr <= NMID; ++lyr) {      // middle layer lyr: chunk j -> the other hidden buffer
+                        const uint32_t col_dst = (lyr & 1) ? COL_HB : COL_H1;
+                        for (int i = 0; i < NC / 2; ++i) {
+                            const int j = 2 * i + (int)pair;
+                            const uint32_t gg = g + j, buf = pair, n = gg >> 1;
+                            wait_t<DBG>(bar + D_FULL + buf, n & 1, c_dfull);
+                            tc_fence_after();
+                            drain32_act<FMT, ACT>(ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base, sb + lyr * HD + j * 64 + half * 32,
+                                                  tmem + col_dst + j * 32 + half * 16 + lane_base, bar_a + 8 * (D_EMPTY + buf), 0u, 0u, nullptr);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_a(bar_a + 8 * H1_FULL);
+                        }
+                        g += NC;
+                    }
+                }
+                for (int i = 0; i < NC / 2; ++i) {               // last hidden layer, chunk j -> an H2 buffer
                     const int j = 2 * i + (int)pair;
                     const uint32_t gg = g + j, buf = pair, n = gg >> 1, cc = c1 + j;
                     // H2 hand-off.  Double buffered: wait until the partial of chunk cc-2 (same buffer, same
@@ -825,7 +855,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                     TRACE(1 + wg, 2000 + j);
                     const long long td = (DBG && g_tc_count_waits) ? clock64() : 0;
                     drain32_act<FMT, ACT>((ACT == 0) ? p.member_act[e * G + j / CPM] : ACT, tmem + COL_D + buf * 64 + half * 32 + lane_base,
-                                      sb + HD + j * 64 + half * 32,
+                                      sb + NHID * HD + j * 64 + half * 32,
                                       tmem + COL_H2 + hb * 32 + half * 16 + lane_base, bar_a + 8 * (D_EMPTY + buf),
                                       h2_free, h2_par, DBG ? dtr : nullptr);
                     if (DBG && m == 8 && lane == 0 && (warp & 3) == 0 && p.dbg && blockIdx.x == 0) {
@@ -869,6 +899,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
 //    (hi, lo) pair of 16-bit values (together ~21 mantissa bits) and the input panel holds 1.0 in those two
 //    columns, which removes the bias add from the drain-bound layer-0 epilogue.  Needs K0 + 2 <= 64.
 struct PackCfg { int fold; int act[CMBPO_MAX_E]; };
+struct PackW { const float* W[CMBPO_MAX_LAYERS]; int n_layers; };     // fp32 master copies, W[n_layers-1] = output layer
 
 template <int FMT> __device__ __forceinline__ uint16_t to16(float v) {
     if (FMT == 0) { __half x = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); return *reinterpret_cast<uint16_t*>(&x); }
@@ -880,18 +911,19 @@ template <int FMT> __device__ __forceinline__ float from16(uint16_t h) {
 }
 
 template <int FMT>
-__global__ void pack_weights_kernel(const float* W0, const float* W1, const float* W2, const float* b0, int K0, int HD,
+__global__ void pack_weights_kernel(PackW pw, const float* b0, int K0, int HD,
                                     int Nout, int E, int group, const Stage* stages, int n_stages,
                                     unsigned long long member_bytes, PackCfg cfg, uint8_t* out) {
     // HD = the REAL hidden width of the fp32 master copy; tiles beyond it (the instantiation's padded width) are zeros
     const Stage st = stages[blockIdx.x];
     const int e = blockIdx.y * group + st.member;        // real member (may be >= E in the last group: zeros)
     const float* W; int K, M;
-    if (st.layer == 0) { W = W0 + (size_t)e * K0 * HD; K = K0; M = HD; }
-    else if (st.layer == 1) { W = W1 + (size_t)e * HD * HD; K = HD; M = HD; }
-    else { W = W2 + (size_t)e * HD * Nout; K = HD; M = Nout; }
+    const int last = pw.n_layers - 1;                    // st.layer indexes the master copies
+    if (st.layer == 0) { W = pw.W[0] + (size_t)e * K0 * HD; K = K0; M = HD; }
+    else if (st.layer < last) { W = pw.W[st.layer] + (size_t)e * HD * HD; K = HD; M = HD; }
+    else { W = pw.W[last] + (size_t)e * HD * Nout; K = HD; M = Nout; }
     if (e >= E) K = 0;
-    const float scale = (st.layer < 2 && e < E && cfg.act[e] == CMBPO_ACT_SWISH) ? 0.5f : 1.0f;
+    const float scale = (st.layer < last && e < E && cfg.act[e] == CMBPO_ACT_SWISH) ? 0.5f : 1.0f;
     uint8_t* dst = out + (size_t)blockIdx.y * member_bytes + st.off;
     for (int idx = threadIdx.x; idx < st.rows * 64; idx += blockDim.x) {
         const int n = idx >> 6, k = idx & 63;
@@ -907,24 +939,21 @@ __global__ void pack_weights_kernel(const float* W0, const float* W1, const floa
     }
 }
 
-// per unit: [b0 of the G members | b1 of the G members | b2 (NP each) of the G members]; HD = member width.
-// The hidden biases of swish members are halved like their weights.
-__global__ void pack_bias_kernel(const float* b0, const float* b1, const float* b2, int HD, int HR, int Nout, int NP,
-                                 int E, int group, PackCfg cfg, float* out) {
-    // HD = padded member width (layout), HR = real width of the master copy
+// per unit: [b_0 of the G members | ... | b_{nh-1} of the G members | b_out (NP each) of the G members]; HD = padded
+// member width (layout), HR = real width of the master copy, nh = number of hidden layers.  The hidden biases of
+// swish members are halved like their weights.
+struct PackB { const float* b[CMBPO_MAX_LAYERS]; int nh; };
+__global__ void pack_bias_kernel(PackB pb, int HD, int HR, int Nout, int NP, int E, int group, PackCfg cfg, float* out) {
     const int u = blockIdx.x;
-    const int stride = group * (2 * HD + NP);
+    const int stride = group * (pb.nh * HD + NP);
     for (int i = threadIdx.x; i < stride; i += blockDim.x) {
         float v = 0.f;
-        if (i < group * HD) {
-            const int e = u * group + i / HD;
-            if (e < E && i % HD < HR) v = b0[(size_t)e * HR + i % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
-        } else if (i < 2 * group * HD) {
-            const int k = i - group * HD, e = u * group + k / HD;
-            if (e < E && k % HD < HR) v = b1[(size_t)e * HR + k % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
+        if (i < pb.nh * group * HD) {
+            const int l = i / (group * HD), k = i - l * group * HD, e = u * group + k / HD;
+            if (e < E && k % HD < HR) v = pb.b[l][(size_t)e * HR + k % HD] * (cfg.act[e] == CMBPO_ACT_SWISH ? 0.5f : 1.0f);
         } else {
-            const int k = i - 2 * group * HD, e = u * group + k / NP, c = k % NP;
-            if (e < E && c < Nout) v = b2[(size_t)e * Nout + c];
+            const int k = i - pb.nh * group * HD, e = u * group + k / NP, c = k % NP;
+            if (e < E && c < Nout) v = pb.b[pb.nh][(size_t)e * Nout + c];
         }
         out[(size_t)u * stride + i] = v;
     }
@@ -943,22 +972,24 @@ OutShape out_shape(int Nout) {
 // the order in which the MMA warp consumes weight tiles (must match the kernel's loops):
 // main stream = layer-0 chunk tiles, then per chunk the layer-1 K-panel tiles; W2 stream = per chunk
 // the layer-2 tile(s)
-void stage_programs(int HD, int NP, int parts, int group, std::vector<Stage>* main_prog,
+void stage_programs(int HD, int NP, int parts, int group, int nhid, std::vector<Stage>* main_prog,
                     unsigned long long* main_bytes, std::vector<Stage>* w2_prog, unsigned long long* w2_bytes) {
+    // nhid = number of HD x HD layers (1 + NMID); Stage.layer indexes the master copies: 0, 1 .. nhid, nhid + 1 = output
     // HD = virtual width of a unit (group * member width); chunk j belongs to member j / CPM
     const int NC = HD / 64, CPM = NC / group, KPm = HD / 64 / group, NPp = NP / parts;
     unsigned long long off = 0;
     for (int j = 0; j < NC; ++j) { main_prog->push_back(Stage{0, (j % CPM) * 64, 0, 64, j / CPM, off}); off += TILE; }
-    for (int j = 0; j < NC; ++j)
-        for (int kp = 0; kp < KPm; ++kp) {
-            main_prog->push_back(Stage{1, (j % CPM) * 64, kp * 64, 64, j / CPM, off});
-            off += TILE;
-        }
+    for (int lyr = 1; lyr <= nhid; ++lyr)
+        for (int j = 0; j < NC; ++j)
+            for (int kp = 0; kp < KPm; ++kp) {
+                main_prog->push_back(Stage{lyr, (j % CPM) * 64, kp * 64, 64, j / CPM, off});
+                off += TILE;
+            }
     *main_bytes = off;
     off = 0;
     for (int j = 0; j < NC; ++j)
         for (int q = 0; q < parts; ++q) {
-            w2_prog->push_back(Stage{2, q * NPp, (j % CPM) * 64, NPp, j / CPM, off});
+            w2_prog->push_back(Stage{nhid + 1, q * NPp, (j % CPM) * 64, NPp, j / CPM, off});
             off += (unsigned long long)NPp * 128;
         }
     *w2_bytes = off;
@@ -972,11 +1003,11 @@ int chunks_per_w2_slot(int HD, int NP, int slot_bytes = W2SLOT) {
     return p2 < NC ? p2 : NC;
 }
 
-template <int HD, int FMT, int ACT, bool DBG, int G = 1, bool FUSE = false>
+template <int HD, int FMT, int ACT, bool DBG, int G = 1, bool FUSE = false, int NMID = 0>
 int launch_tc(cmbpo_ctx* ctx, const TcParams& p) {
     const int smem = (FUSE ? SMEM_TOTAL_F : SMEM_TOTAL) + 1024 + (DBG ? 1968 : 0);
     static_assert(SMEM_TOTAL + 1024 + 1968 <= 232448, "shared memory budget");
-    auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT, DBG, G, FUSE>;
+    auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT, DBG, G, FUSE, NMID>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const long long units = (long long)p.ntiles * ((p.E + G - 1) / G);
     const int grid = units < ctx->sm_count ? (int)units : ctx->sm_count;
@@ -1001,6 +1032,16 @@ int launch_tc_act(cmbpo_ctx* ctx, const TcParams& p, int act) {
     return launch_tc<HD, FMT, CMBPO_ACT_TANH, false>(ctx, p);
 }
 
+// 3 / 4 hidden layers at (padded) width 256
+template <int FMT>
+int launch_tc_deep(cmbpo_ctx* ctx, const TcParams& p, int act, int nmid) {
+    if (act == CMBPO_ACT_SWISH)
+        return nmid == 1 ? launch_tc<256, FMT, CMBPO_ACT_SWISH, false, 1, false, 1>(ctx, p)
+                         : launch_tc<256, FMT, CMBPO_ACT_SWISH, false, 1, false, 2>(ctx, p);
+    return nmid == 1 ? launch_tc<256, FMT, CMBPO_ACT_TANH, false, 1, false, 1>(ctx, p)
+                     : launch_tc<256, FMT, CMBPO_ACT_TANH, false, 1, false, 2>(ctx, p);
+}
+
 template <int FMT>
 int launch_tc_grouped(cmbpo_ctx* ctx, const TcParams& p, int act) {       // 4 members of width 128 per unit
     if (act == 0) return launch_tc<512, FMT, 0, false, 4>(ctx, p);
@@ -1018,27 +1059,36 @@ int launch_tc_hd(cmbpo_ctx* ctx, const TcParams& p, int hd, int act) {
 
 }  // namespace
 
+// 2 hidden layers: any equal width <= 512 (padded to 128 / 256 / 512), <= 64 inputs, <= 128 outputs.
+// 3 or 4 hidden layers (e.g. the (200,200,200,200) default of algorithms/cmbpo.py:54): equal width <= 256, <= 64 outputs
+// (tensor-memory budget of the second hidden buffer).
 bool ens_tc_supported(const Net& n) {
-    if (!n.loaded || n.n_layers != 3) return false;
-    const int hd = n.dims[1];
-    if (n.dims[2] != hd || hd < 1 || hd > 512) return false;      // any width <= 512 (padded to 128 / 256 / 512)
-    if (n.dims[0] > 64 || n.dims[3] > 128) return false;
-    if (n.acts[0] != n.acts[1] || n.acts[2] != CMBPO_ACT_NONE) return false;
+    if (!n.loaded || n.n_layers < 3 || n.n_layers > 5) return false;
+    const int hd = n.dims[1], L = n.n_layers;
+    for (int l = 1; l < L; ++l) if (n.dims[l] != hd) return false;
+    if (hd < 1 || hd > (L == 3 ? 512 : 256)) return false;
+    if (n.dims[0] > 64 || n.dims[L] > (L == 3 ? 128 : 64)) return false;
+    for (int l = 1; l < L - 1; ++l) if (n.acts[l] != n.acts[0]) return false;
+    if (n.acts[L - 1] != CMBPO_ACT_NONE) return false;
     return n.acts[0] == CMBPO_ACT_SWISH || n.acts[0] == CMBPO_ACT_TANH;
 }
 
 // pack both 16-bit formats once per weight upload: [main stream | W2 stream] per precision
 int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
-    const int HR = net.dims[1], HD = padded_hd(HR), K0 = net.dims[0], Nout = net.dims[3];
+    const int L = net.n_layers, nhid = L - 2;            // HD x HD layers
+    const int HR = net.dims[1], HD = (nhid > 1) ? 256 : padded_hd(HR), K0 = net.dims[0], Nout = net.dims[L];
     net.tc_hd = HD;
     const OutShape os = out_shape(Nout);
     // narrow ensembles run grouped: 4 members of width 128 per unit (their OUT blocks share 64 columns)
-    const int group = (HD == 128 && net.E >= 2 && os.NP <= 16) ? 4 : 1;
+    const int group = (nhid == 1 && HD == 128 && net.E >= 2 && os.NP <= 16) ? 4 : 1;
     const int n_units = (net.E + group - 1) / group;
     net.tc_group = group;
     unsigned long long main_bytes = 0, w2_bytes = 0;
     std::vector<Stage> mp, wp;
-    stage_programs(HD * group, os.NP, os.parts, group, &mp, &main_bytes, &wp, &w2_bytes);
+    stage_programs(HD * group, os.NP, os.parts, group, nhid, &mp, &main_bytes, &wp, &w2_bytes);
+    PackW pw; PackB pb;
+    pw.n_layers = L; pb.nh = L - 1;
+    for (int l = 0; l < CMBPO_MAX_LAYERS; ++l) { pw.W[l] = net.W[l]; pb.b[l] = net.b[l]; }
     PackCfg pc;
     pc.fold = (K0 + 2 <= 64) ? 1 : 0;
     for (int e = 0; e < CMBPO_MAX_E; ++e) pc.act[e] = net.member_act[0] >= 0 ? net.member_act[e] : net.acts[0];
@@ -1056,15 +1106,15 @@ int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
         uint8_t* base2 = base + (size_t)n_units * main_bytes;
         dim3 g1((unsigned)mp.size(), n_units), g2((unsigned)wp.size(), n_units);
         if (prec == CMBPO_PREC_FP16) {
-            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HR, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
-            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HR, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
+            pack_weights_kernel<0><<<g1, 256, 0, ctx->stream>>>(pw, net.b[0], K0, HR, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
+            pack_weights_kernel<0><<<g2, 256, 0, ctx->stream>>>(pw, net.b[0], K0, HR, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
         } else {
-            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HR, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
-            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(net.W[0], net.W[1], net.W[2], net.b[0], K0, HR, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
+            pack_weights_kernel<1><<<g1, 256, 0, ctx->stream>>>(pw, net.b[0], K0, HR, Nout, net.E, group, d_mp, (int)mp.size(), main_bytes, pc, base);
+            pack_weights_kernel<1><<<g2, 256, 0, ctx->stream>>>(pw, net.b[0], K0, HR, Nout, net.E, group, d_wp, (int)wp.size(), w2_bytes, pc, base2);
         }
     }
-    CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)n_units * group * (2 * HD + os.NP) * sizeof(float)));
-    pack_bias_kernel<<<n_units, 256, 0, ctx->stream>>>(net.b[0], net.b[1], net.b[2], HD, HR, Nout, os.NP, net.E, group, pc, net.tc_bias);
+    CUDA_TRY(cudaMalloc(&net.tc_bias, (size_t)n_units * group * ((L - 1) * HD + os.NP) * sizeof(float)));
+    pack_bias_kernel<<<n_units, 256, 0, ctx->stream>>>(pb, HD, HR, Nout, os.NP, net.E, group, pc, net.tc_bias);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaFree(d_mp));
     CUDA_TRY(cudaFree(d_wp));
@@ -1074,7 +1124,7 @@ int ens_tc_prepare(cmbpo_ctx* ctx, Net& net) {
 
 // the conditions under which cmbpo_rollout may fuse the step around this ensemble's GEMM chain
 bool ens_tc_fusable(const Net& n) {
-    if (!ens_tc_supported(n) || n.tc_group != 1 || n.E != 7 || !n.probabilistic) return false;
+    if (!ens_tc_supported(n) || n.n_layers != 3 || n.tc_group != 1 || n.E != 7 || !n.probabilistic) return false;
     if (n.acts[0] != CMBPO_ACT_SWISH || n.member_act[0] >= 0) return false;
     const OutShape os = out_shape(n.dims[3]);
     return os.NP * 128 <= W2SLOT_F && n.D <= 64;       // one chunk's layer-2 tiles must fit a (shrunk) ring slot
@@ -1097,9 +1147,10 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     if (N <= 0) return 0;
     CMBPO_CHECK((N + 127) / 128 * (int64_t)net.E < (int64_t)1 << 31, "too many rows for one launch");
     const int HD = net.tc_hd;                   // padded hidden width = kernel instantiation
-    const OutShape os = out_shape(net.dims[3]);
+    const int nmid = net.n_layers - 3;          // middle hidden layers (deep variant)
+    const OutShape os = out_shape(net.dims[net.n_layers]);
     TcParams p;
-    p.Nout = net.dims[3];
+    p.Nout = net.dims[net.n_layers];
     p.NP = os.NP; p.parts = os.parts;
     p.cps = chunks_per_w2_slot(HD * net.tc_group, os.NP, fz ? W2SLOT_F : W2SLOT);
     p.wmain = (const uint8_t*)net.tc_pack[precision];
@@ -1107,7 +1158,7 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
     p.w2 = p.wmain + (size_t)((net.E + net.tc_group - 1) / net.tc_group) * p.main_bytes;
     p.w2_bytes = (unsigned long long)(HD * net.tc_group / 64) * p.NP * 128;
     const int group = net.tc_group, n_units = (net.E + group - 1) / group;
-    p.bias = net.tc_bias; p.bias_stride = group * (2 * HD + p.NP);
+    p.bias = net.tc_bias; p.bias_stride = group * ((net.n_layers - 1) * HD + p.NP);
     p.E = net.E; p.K0 = net.dims[0]; p.fold = net.tc_fold; p.KS0 = (p.K0 + (p.fold ? 2 : 0) + 15) / 16;
     p.x = x; p.N = N; p.ldx = net.dims[0];
     p.n_dev = reinterpret_cast<const long long*>(n_dev);
@@ -1167,6 +1218,10 @@ int ens_forward_tc(cmbpo_ctx* ctx, Net& net, const float* x, int64_t N, float* o
         return 0;
     }
     (void)n_units;
+    if (nmid > 0) {
+        CMBPO_CHECK(HD == 256 && group == 1 && (nmid == 1 || nmid == 2) && net.member_act[0] < 0, "deep tcgen05 variant: bad shape");
+        return precision == CMBPO_PREC_FP16 ? launch_tc_deep<0>(ctx, p, act_sel, nmid) : launch_tc_deep<1>(ctx, p, act_sel, nmid);
+    }
     if (group == 4) return precision == CMBPO_PREC_FP16 ? launch_tc_grouped<0>(ctx, p, act_sel) : launch_tc_grouped<1>(ctx, p, act_sel);
     if (precision == CMBPO_PREC_FP16) return launch_tc_hd<0>(ctx, p, HD, act_sel);
     return launch_tc_hd<1>(ctx, p, HD, act_sel);

@@ -31,7 +31,7 @@ class B200PE:
                            probabilistic, self._model_inds)
 
     @classmethod
-    def from_oracle_ensemble(cls, engine, which, ens, name="PE"):
+    def from_arrays(cls, engine, which, ens, name="PE"):
         """Build from a plain container with fields W, b, acts, probabilistic, mu_in, ..."""
         return cls(engine, which, ens.W, ens.b, ens.acts, ens.probabilistic, ens.elite_inds,
                    ens.mu_in, ens.var_in, ens.mu_out, ens.var_out, name=name)

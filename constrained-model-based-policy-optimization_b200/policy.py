@@ -41,8 +41,8 @@ class B200Policy:
         self.vc = B200PE.view(self.engine, L.NET_VC, name="VCEnsemble")
 
     def load_values(self, v_ens, vc_ens):
-        self.v = B200PE.from_oracle_ensemble(self.engine, L.NET_V, v_ens, name="VEnsemble")
-        self.vc = B200PE.from_oracle_ensemble(self.engine, L.NET_VC, vc_ens, name="VCEnsemble")
+        self.v = B200PE.from_arrays(self.engine, L.NET_V, v_ens, name="VEnsemble")
+        self.vc = B200PE.from_arrays(self.engine, L.NET_VC, vc_ens, name="VCEnsemble")
 
     def reset(self):
         pass

@@ -11,7 +11,7 @@ GAE = dict(gamma=0.99, lam=0.95, cost_gamma=0.97, cost_lam=0.5)
 def load_problem(engine, dyn, actor, v, vc):
     import cmbpo_b200 as cb
     from cmbpo_b200 import _lib as L
-    model = cb.B200PE.from_oracle_ensemble(engine, L.NET_DYN, dyn, name="DynEns")
+    model = cb.B200PE.from_arrays(engine, L.NET_DYN, dyn, name="DynEns")
     policy = cb.B200Policy(engine)
     policy.load_actor(actor.W, actor.b, actor.log_std)
     policy.load_values(v, vc)

@@ -15,7 +15,7 @@ def test_loaded_checkpoint_predicts_like_direct_upload(engine, tmp_path):
     dyn, actor, v, vc = orc.make_problem(11, 17, 6, hidden=(64, 64))
     obs, act = orc.make_states(12, 300, 17, 6, dyn)
     x = np.concatenate([obs, act], -1)
-    direct = cb.B200PE.from_oracle_ensemble(engine, L.NET_DYN, dyn)
+    direct = cb.B200PE.from_arrays(engine, L.NET_DYN, dyn)
     m0, v0 = direct.predict_ensemble(x)
     write_like_pe_save(str(tmp_path), "BNN", 7, dyn, ("in", "out"), nll=True)
     loaded = cb.load_pe(engine, L.NET_DYN, str(tmp_path), "BNN", 7, elite_inds=dyn.elite_inds)

@@ -299,6 +299,12 @@ def test_return_arrays_and_get_device(engine):
         if device:
             out, diag = pool.get_device()
             assert all(hasattr(x, "is_cuda") and x.is_cuda for x in out)
+            # consumer hand-off through the DLPack protocol: a consumer that only speaks DLPack
+            # sees the same device memory (zero copy), including the stride-0 log_std view
+            import torch
+            for x in out:
+                y = torch.from_dlpack(x.__dlpack__())
+                assert y.data_ptr() == x.data_ptr() and y.shape == x.shape and torch.equal(y, x)
             out = [x.cpu().numpy() for x in out]
             pool.reset()
         else:

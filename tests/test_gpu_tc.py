@@ -106,16 +106,22 @@ def test_rollout_tc_other_ensemble_shapes(engine, num_nets, hidden, B):
 
 @pytest.mark.parametrize("key,O,hidden,B", [("hcs", 17, (200, 200), 500), ("hcs", 20, (512, 512), 300),
                                             ("ant", 29, (300, 300), 257), ("hcs", 20, (64, 64), 100),
-                                            ("hum", 47, (200, 200), 130)])
+                                            ("hum", 47, (200, 200), 130),
+                                            ("hcs", 17, (200, 200, 200, 200), 700), ("ant", 29, (128, 128, 128), 129),
+                                            ("hcs", 20, (256, 256, 256), 5000)])
 def test_rollout_tc_padded_widths_and_real_hcs_obs(engine, key, O, hidden, B):
     """Hidden widths that are not a kernel instantiation (200, 300, 64: zero padded to 256 / 512 / 128 at pack
-    time) and the O = 20 observation of the real HalfCheetahSafe environment (the kernels must
+    time), three and four hidden layers (the (200,200,200,200) code default of algorithms/cmbpo.py:54: the deep
+    tcgen05 variant with two hidden buffers in tensor memory) and the O = 20 observation of the real HalfCheetahSafe environment (the kernels must
     be generic in O / A): single-step prediction against the oracle within the tolerance of test_predict_ensemble_tc,
     and a short rollout against the fp32 CUDA-core path."""
     import cmbpo_b200 as cb
     task, _, A = TASKS[key]
     T = 6
     dyn, actor, v, vc = orc.make_problem(61, O, A, hidden=hidden, task=task)
+    rb = np.random.default_rng(60)
+    for bl in dyn.b:                                  # non-zero biases: the packed bias layout of every layer matters
+        bl += (0.1 * rb.standard_normal(bl.shape)).astype(np.float32)
     obs, act = orc.make_states(62, B, O, A, dyn)
     model, policy = load_problem(engine, dyn, actor, v, vc)
     x = np.concatenate([obs, act], axis=1)

@@ -26,7 +26,7 @@ def _setup(engine, seed, E, bs, O, A, hidden, prob=True):
         ens, which, Din, D = v, L.NET_V, O, 1
     for bl in ens.b:                                   # non-zero biases so that their gradients matter
         bl += 0.05 * rng.standard_normal(bl.shape).astype(np.float32)
-    model = cb.B200PE.from_oracle_ensemble(engine, which, ens)
+    model = cb.B200PE.from_arrays(engine, which, ens)
     x = (rng.standard_normal((E, bs, Din)) * np.maximum(np.sqrt(ens.var_in), 1e-2) + ens.mu_in).astype(np.float32)
     y = (rng.standard_normal((E, bs, D)) * np.maximum(np.sqrt(ens.var_out), 1e-2) + ens.mu_out).astype(np.float32)
     return model, ens, which, x, y
@@ -93,7 +93,7 @@ def test_train_loop_learns_and_repacks(engine):
     O, A, E = 17, 6, 7
     rng = np.random.RandomState(0)
     dyn, _, _, _ = orc.make_problem(21, O, A, hidden=(128, 128), num_nets=E, num_elites=5, gain=1.0)
-    model = cb.B200PE.from_oracle_ensemble(engine, L.NET_DYN, dyn)
+    model = cb.B200PE.from_arrays(engine, L.NET_DYN, dyn)
     n = 4096
     X = rng.standard_normal((n, O + A)).astype(np.float32)
     M = (rng.standard_normal((O + A, O + 1)) * 0.3).astype(np.float32)

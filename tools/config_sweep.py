@@ -14,7 +14,7 @@ B, T = 100000, 35
 for key, (task, O, A, term, cost) in CFG.items():
     dyn, actor, v, vc = wl.make_problem(0, O, A, hidden=(512, 512), task=task)
     eng = cb.Engine(0, precision="fp16")
-    cb.B200PE.from_oracle_ensemble(eng, L.NET_DYN, dyn)
+    cb.B200PE.from_arrays(eng, L.NET_DYN, dyn)
     pol = cb.B200Policy(eng); pol.load_actor(actor.W, actor.b, actor.log_std); pol.load_values(v, vc)
     obs, _ = wl.make_states(1, B, O, A, dyn)
     bufs = cb.RolloutBuffers(eng, B, T, O, A)

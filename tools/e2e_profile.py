@@ -10,7 +10,7 @@ from cmbpo_b200 import workload as orc   # synthetic problem generator (no test 
 B, T, O, A = 100000, 35, 17, 6
 dyn, actor, v, vc = orc.make_problem(0, O, A, hidden=(512, 512))
 eng = cb.Engine(0, precision="fp16")
-model = cb.B200PE.from_oracle_ensemble(eng, L.NET_DYN, dyn)
+model = cb.B200PE.from_arrays(eng, L.NET_DYN, dyn)
 policy = cb.B200Policy(eng); policy.load_actor(actor.W, actor.b, actor.log_std); policy.load_values(v, vc)
 class S:
     def __init__(s, n): s.shape = (n,)

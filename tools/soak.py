@@ -14,12 +14,12 @@ t0 = time.time()
 n_roll = 0
 for it in range(12):
     task, O, A, term, cost = TASKS[it % 3]
-    hidden = [(512, 512), (256, 256), (128, 128)][int(rng.integers(3))]
+    hidden = [(512, 512), (256, 256), (128, 128), (200, 200), (300, 300), (64, 64)][int(rng.integers(6))]
     E = int(rng.choice([3, 5, 7]))
     dyn, actor, v, vc = wl.make_problem(it, O, A, hidden=hidden, num_nets=E, num_elites=max(1, E - 2), task=task)
     prec = ["fp16", "bf16"][it % 2]
     eng = cb.Engine(0, precision=prec)
-    cb.B200PE.from_oracle_ensemble(eng, L.NET_DYN, dyn)
+    cb.B200PE.from_arrays(eng, L.NET_DYN, dyn)
     pol = cb.B200Policy(eng); pol.load_actor(actor.W, actor.b, actor.log_std); pol.load_values(v, vc)
     cfg = L.EnvCfg(term, cost, 0, 1, 1)
     for rep in range(10):

@@ -11,7 +11,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 dyn, actor, v, vc = orc.make_problem(0, 17, 6, hidden=(512, 512))
 eng = cb.Engine(0, precision="fp16")
 L.check(eng.lib.cmbpo_ctx_set_debug(eng.h, int(os.environ.get("CMBPO_TC_DEBUG", "0")), int(os.environ.get("CMBPO_TC_TRACE_ONLY", "0"))))
-model = cb.B200PE.from_oracle_ensemble(eng, L.NET_DYN, dyn)
+model = cb.B200PE.from_arrays(eng, L.NET_DYN, dyn)
 obs, act = orc.make_states(1, N, 17, 6, dyn)
 x = eng.to_device(np.concatenate([obs, act], -1))
 for i in range(3):

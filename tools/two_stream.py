@@ -15,7 +15,7 @@ cfg = L.EnvCfg(L.TERM_NO_DONE, L.COST_HCS, 0, 1, 1)
 def make(nB, stream):
     with torch.cuda.stream(stream):
         eng = cb.Engine(0, precision="fp16")
-        cb.B200PE.from_oracle_ensemble(eng, L.NET_DYN, dyn)
+        cb.B200PE.from_arrays(eng, L.NET_DYN, dyn)
         pol = cb.B200Policy(eng); pol.load_actor(actor.W, actor.b, actor.log_std); pol.load_values(v, vc)
         bufs = cb.RolloutBuffers(eng, nB, T, O, A)
     return eng, bufs

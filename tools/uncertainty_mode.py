@@ -11,7 +11,7 @@ from cmbpo_b200 import workload as wl
 B, T, O, A = 100000, 35, 17, 6
 dyn, actor, v, vc = wl.make_problem(0, O, A, hidden=(512, 512))
 eng = cb.Engine(0, precision="fp16")
-model = cb.B200PE.from_oracle_ensemble(eng, L.NET_DYN, dyn)
+model = cb.B200PE.from_arrays(eng, L.NET_DYN, dyn)
 pol = cb.B200Policy(eng); pol.load_actor(actor.W, actor.b, actor.log_std); pol.load_values(v, vc)
 obs, act = wl.make_states(1, B, O, A, dyn)
 cfg = L.EnvCfg(L.TERM_NO_DONE, L.COST_HCS, 0, 1, 1)
