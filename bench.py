@@ -118,6 +118,31 @@ def ncu_tensor_pipe():
     return None
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's process to the CPU cores NVML reports as local to its GPU, so that page-locked host buffers
+    (first touched by this process) and the D2H copies stay on the GPU's NUMA node.  Returns the core count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                phys = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks
     line), through NVML in a thread (initialised before the region starts: spawning nvidia-smi takes
@@ -453,6 +478,7 @@ def run_cuda(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
+    args.numa_cores = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = CONFIGS[args.config]
@@ -569,8 +595,9 @@ def bench_hcs(rig, args, cfg):
     if not args.no_e2e:
         pairs = [make_pair(0), make_pair(1)]
         torch.cuda.synchronize()
-        for _ in range(max(2, min(args.warmup, 3))):
-            plain_batch(pairs[0])
+        out = None
+        for _ in range(max(3, min(args.warmup, 5))):     # (holding the previous batch like the timed loop does, so
+            out = plain_batch(pairs[0])                  #  that both generations of page-locked blocks exist)
         rig.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -580,6 +607,35 @@ def bench_hcs(rig, args, cfg):
         plain_s = time.perf_counter() - t0
         d2h_plain = d2h_bytes(out)
         del out
+        # per-rank timeline of the plain sequence (5 more batches, outside the timed e2e region): where a batch's
+        # host wall time goes -- waiting for the rollout, statistics (+ all-reduce) / compaction, the D2H copy
+        tl = np.zeros(5)
+        smp, pool, _ = pairs[0]
+        for _ in range(5):
+            ta = time.perf_counter()
+            smp.reset(obs_host)
+            tb = time.perf_counter()
+            while True:
+                _, _, _, info = smp.sample(None)
+                if info["alive_ratio"] <= 0.1:
+                    break
+            smp.finish_all_paths()
+            tc_ = time.perf_counter()
+            dev_out, _ = pool.get_device()
+            torch.cuda.synchronize()
+            td = time.perf_counter()
+            host_out = pool.to_host(dev_out)
+            te = time.perf_counter()
+            pool.reset()
+            tl += np.array([tb - ta, tc_ - tb, td - tc_, te - td, te - ta]) * 1e3 / 5
+            del host_out, dev_out
+        timeline = torch.tensor(tl, device=dev, dtype=torch.float64)
+        if world > 1:
+            gathered = [torch.zeros_like(timeline) for _ in range(world)]
+            rig.dist.all_gather(gathered, timeline)
+        else:
+            gathered = [timeline]
+        timeline_rows = [[round(float(x), 3) for x in g] for g in gathered]
         pipelined_run(pairs, 4)             # warm-up: page-locked buffer sets of both pairs get allocated
         rig.barrier()
         t0 = time.perf_counter()
@@ -625,6 +681,13 @@ def bench_hcs(rig, args, cfg):
                        "d2h_bytes_per_step": int(d2h_plain), "batches": args.steps,
                        "api": "the unmodified caller's sequence (cmbpo.py:251-269): ModelSampler.reset / sample / "
                               "finish_all_paths + blocking ModelBuffer.get(), numpy in, caller-owned numpy out, one pair"}
+        d2h_ms = float(np.mean([r[3] for r in timeline_rows]))
+        line["e2e_timeline"] = {"columns": ["reset_h2d_ms", "rollout_wait_sample_finish_ms", "stats_allreduce_compact_ms",
+                                            "d2h_ms", "total_ms"], "per_rank": timeline_rows,
+                                "d2h_GBps_per_rank": d2h_plain / (d2h_ms * 1e-3) / 1e9 if d2h_ms > 0 else None,
+                                "d2h_GBps_aggregate": world * d2h_plain / (d2h_ms * 1e-3) / 1e9 if d2h_ms > 0 else None,
+                                "numa_local_cores": args.numa_cores,
+                                "note": "5 batches of the plain sequence per rank, host wall clock per stage"}
         line["e2e_pipelined"] = {"value": pipe_n / pipe_s, "unit": UNIT, "h2d_bytes_per_step": int(obs_host.nbytes),
                                  "d2h_bytes_per_step": int(d2h_pipe), "batches": args.steps,
                                  "api": "two sampler+buffer pairs alternating with ModelBuffer.get_async().result() "
@@ -824,6 +887,7 @@ def main():
                     help="transition mode: deterministic mean (reference behaviour) or mean + std*eps")
     ap.add_argument("--fuse", action="store_true", help="use the fused rollout step (CMBPO_ROLLOUT_FUSE)")
     ap.add_argument("--total", type=int, default=0, help="ant1m: total start states (default 1,000,000)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin ranks to their GPU's NUMA-local cores")
     ap.add_argument("--sweep-h", default="1,2,5,10,20,30")
     ap.add_argument("--sweep-b", default="10000,100000,1000000,4000000")
     args = ap.parse_args()

@@ -200,26 +200,29 @@ class ModelBuffer:
         faulted again: ~50 GB/s instead of the ~3 GB/s of fresh pageable arrays.  `pinned=False`: plain pageable
         `.cpu()` copies."""
         out, diag = self.get_device()
+        res = self.to_host(out, pinned)
+        self.reset()
+        return res, diag
+
+    def to_host(self, out, pinned=True):
+        """The device->host half of get(): the 12 device tensors of get_device() as numpy arrays."""
         # log_std (index 10) is one [A] row repeated: it crosses PCIe once and is returned as a
         # read-only broadcast view (values, shape and dtype as the reference's array)
         ls_host = np.broadcast_to(out[10][:1].cpu().numpy().reshape(1, -1) if out[10].shape[0] else
                                   np.zeros((1, self.act_dim), np.float32), tuple(out[10].shape))
         if not pinned:
-            res = [ls_host if i == 10 else x.cpu().numpy() for i, x in enumerate(out)]
-        else:
-            t = self.engine.torch
-            host = []
-            for i, x in enumerate(out):
-                if i == 10:
-                    host.append(None)
-                    continue
-                h = t.empty(tuple(x.shape), dtype=x.dtype, pin_memory=True)
-                h.copy_(x, non_blocking=True)
-                host.append(h)
-            t.cuda.current_stream(self.engine.device).synchronize()
-            res = [ls_host if h is None else h.numpy() for h in host]
-        self.reset()
-        return res, diag
+            return [ls_host if i == 10 else x.cpu().numpy() for i, x in enumerate(out)]
+        t = self.engine.torch
+        host = []
+        for i, x in enumerate(out):
+            if i == 10:
+                host.append(None)
+                continue
+            h = t.empty(tuple(x.shape), dtype=x.dtype, pin_memory=True)
+            h.copy_(x, non_blocking=True)
+            host.append(h)
+        t.cuda.current_stream(self.engine.device).synchronize()
+        return [ls_host if h is None else h.numpy() for h in host]
 
     def get_async(self):
         """`get()` split in two so that the device->host copy of this batch overlaps the NEXT
