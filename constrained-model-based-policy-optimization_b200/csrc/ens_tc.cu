@@ -330,8 +330,15 @@ __device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, const f
 // padded width <= 256 and NP <= 64.  No extra barriers: the tensor pipe executes in order, so by the time a
 // chunk's accumulator is handed to the epilogue every MMA that read the buffer it is about to overwrite has
 // finished; H1_FULL simply completes once per hidden layer instead of once per unit.
-template <int HD, int FMT, int ACT, bool DBG, int G, bool FUSE, int NMID = 0>
+// CL == 2: the CTAs run as CLUSTER PAIRS that stream ONE copy of the weights from L2: both CTAs of a pair work on
+// the same member (two neighbouring row tiles), each fetches half of every main-ring stage and MULTICASTS it into
+// both CTAs' rings.  Why: the layer-1 phase needs a 2 KB weight tile per 32-cycle MMA = 64 B/clk per SM, and 148 SMs
+// x 64 B/clk is more than the L2 slices deliver (~6300 B/clk chip-wide = 42 B/clk per SM, B300_MICROARCH.md):
+// the phase ran at ~47 cycles per MMA.  Everything else (MMAs, tensor memory, epilogue) stays per CTA (cta_group::1);
+// only a ring slot's release is a pair-wide event (both issuers commit to both CTAs' W_EMPTY barriers).
+template <int HD, int FMT, int ACT, bool DBG, int G, bool FUSE, int NMID = 0, int CL = 1>
 __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams p) {
+    static_assert(CL == 1 || (CL == 2 && G == 1 && !FUSE && !DBG), "cluster pairs: ordinary ensembles only");
     static_assert(!FUSE || (G == 1 && !DBG), "the fused step kernel exists for ordinary (ungrouped) ensembles");
     static_assert(NMID == 0 || (HD <= 256 && G == 1 && !FUSE && !DBG), "deep variant: width <= 256, ungrouped");
     constexpr int W2S = FUSE ? W2SLOT_F : W2SLOT;          // layer-2 ring slot bytes
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     const int NPp = p.NP / p.parts;
     const uint32_t w2_chunk_bytes = (uint32_t)p.NP * 128u;     // all parts of one chunk
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NSM; ++i) { mbar_init(bar + W_FULL + i, 1); mbar_init(bar + W_EMPTY + i, 1); }
+        for (int i = 0; i < NSM; ++i) { mbar_init(bar + W_FULL + i, 1); mbar_init(bar + W_EMPTY + i, CL); }
         for (int i = 0; i < NS2; ++i) { mbar_init(bar + W2_FULL + i, 1); mbar_init(bar + W2_EMPTY + i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar + D_FULL + i, 1); mbar_init(bar + D_EMPTY + i, 8);
@@ -382,6 +389,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL == 2) cluster_sync_all();      // the peer's barriers are initialised before anything is sent to them
+    const uint32_t cta_rank = (CL == 2) ? cluster_ctarank() : 0u;
     // The CTA owns all 512 columns, so the allocation can only start at lane 0 / column 0.  Treating
     // the base as the constant 0 keeps every MMA operand address in uniform registers (a base read
     // back from shared memory forces a per-instruction R2UR waterfall, ~100 cycles per MMA).
@@ -395,8 +404,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     // the live row count may sit in device memory (alive-row compaction of the rollout): rows beyond
     // it are not computed; strides still use the allocated N
     const long long n_rows = p.n_dev ? *p.n_dev : p.N;
-    const long long n_units = ((n_rows + 127) / 128) * n_groups;      // < 2^31 (checked by the host)
-    const int u0 = (int)(n_units * blockIdx.x / gridDim.x), u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
+    // CL == 2: a unit is (PAIR of row tiles, member), split over the cluster pairs; CTA r of a pair takes tile 2 tp + r
+    // (an odd tile count leaves the last pair one tile without rows: it runs the protocol and stores nothing)
+    const long long n_units = ((n_rows + 128 * CL - 1) / (128 * CL)) * n_groups;      // < 2^31 (checked by the host)
+    const long long w_idx = blockIdx.x / CL, w_cnt = gridDim.x / CL;
+    const int u0 = (int)(n_units * w_idx / w_cnt), u1 = (int)(n_units * (w_idx + 1) / w_cnt);
+#define CMBPO_TILE_OF(u) ((int)((u) / n_groups) * CL + (int)cta_rank)
 
     // (The pool is the CTA's own allocation of 640 x 96 registers: the 128 x (96 - 32) released by the
     // control warpgroup are exactly the 4 x 128 x 16 the epilogue warpgroups request; asking for more
@@ -419,8 +432,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                 auto push = [&](uint32_t bytes) {
                     wait_t<DBG>(bar + W_EMPTY + s, ph ^ 1, c_wempty);
                     if (elect_one()) {
+#ifdef CMBPO_EXP_HALF_W   // timing experiment only (wrong results): half the L2 -> shared-memory bytes
+                        mbar_expect_tx(bar + W_FULL + s, bytes / 2);
+                        bulk_g2s(sW + s * STAGE, src, bytes / 2, bar + W_FULL + s);
+#else
                         mbar_expect_tx(bar + W_FULL + s, bytes);
-                        bulk_g2s(sW + s * STAGE, src, bytes, bar + W_FULL + s);
+                        if (CL == 2)      // my half of the stage, into both CTAs' rings; the peer sends the other half
+                            bulk_g2s_mc(sW + s * STAGE + cta_rank * (bytes / 2), src + cta_rank * (bytes / 2), bytes / 2,
+                                        bar + W_FULL + s, (uint16_t)3);
+                        else
+                            bulk_g2s(sW + s * STAGE, src, bytes, bar + W_FULL + s);
+#endif
                     }
                     __syncwarp();
                     src += bytes;
@@ -528,7 +550,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         if (!SINGLE || elect_one()) {
         int cur_tile = -1;
         for (int u = u0; u < u1; ++u) {
-            const int tile = (int)(u / n_groups);
+            const int tile = CMBPO_TILE_OF(u);
             if (tile != cur_tile) {                 // a new row tile: its XA panel must have landed
                 cur_tile = tile;
                 wait_t<DBG>(bar + X_FULL, it & 1, c_x);
@@ -550,7 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                             for (int ks = 0; ks < p.KS0; ++ks)
                                 mma_f16(tmem + COL_D + buf * 64, dXA + 2 * ks, dB + 2 * ks, idesc_h, ks > 0);
                             mma_commit(bar + D_FULL + buf);
-                            if (jj == G0 - 1) mma_commit(bar + W_EMPTY + s);
+                            if (jj == G0 - 1) { if (CL == 2) mma_commit_mc(bar + W_EMPTY + s, 3); else mma_commit(bar + W_EMPTY + s); }
                         }
                         if (!SINGLE) __syncwarp();
                         TRACE(0, 100 + j0 + jj);
@@ -591,7 +613,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                             // TPS tiles x 4 K-steps from one asm statement (addresses chained inside, see tc_common.cuh)
                             mma_f16_ts_tiles<TPS>(tmem + COL_D + buf * 64, tmem_rt + col_a + ((j / CPM) * KP + kq * TPS) * 32,
                                                   dW0 + (uint64_t)((s * STAGE) >> 4), idesc_h, kq > 0);
-                            mma_commit(bar + W_EMPTY + s);
+                            if (CL == 2) mma_commit_mc(bar + W_EMPTY + s, 3); else mma_commit(bar + W_EMPTY + s);
                             if (kq == KP / TPS - 1) mma_commit(bar + D_FULL + buf);
                         }
                         if (!SINGLE) __syncwarp();
@@ -718,7 +740,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         int cur_tile = -1;
         long long grow = 0;
         for (int u = u0; u < u1; ++u) {
-            const int tile = (int)(u / n_groups);
+            const int tile = CMBPO_TILE_OF(u);
             const bool new_tile = tile != cur_tile;
             cur_tile = tile;
             grow = (long long)tile * 128 + row;
@@ -883,6 +905,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();      // the peer may still be signalling this CTA's barriers
+#undef CMBPO_TILE_OF
     if (DBG && p.dbg && blockIdx.x == 0)
         for (int i = threadIdx.x; i < TRACE_STREAMS * TRACE_WORDS; i += NTHREADS) p.dbg[4096 + i] = trace_smem[i];
     if (warp == 2) tmem_dealloc(tmem, 512);
@@ -1017,6 +1041,36 @@ int launch_tc(cmbpo_ctx* ctx, const TcParams& p) {
     return 0;
 }
 
+// cluster pairs (CL = 2, see the kernel): wide ordinary ensembles with enough row tiles.  The number of co-resident
+// pairs is asked of the runtime once per kernel (a GPC with an odd SM count leaves one SM without a partner).
+template <int HD, int FMT, int ACT>
+int launch_tc_pairs(cmbpo_ctx* ctx, const TcParams& p) {
+    const int smem = SMEM_TOTAL + 1024;
+    auto kern = ens_mlp3_tc_kernel<HD, FMT, ACT, false, 1, false, 0, 2>;
+    static int max_pairs = -1;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (max_pairs < 0) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cfg.gridDim = dim3(2 * (ctx->sm_count / 2));
+        int n = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        max_pairs = n < 1 ? 0 : (n > ctx->sm_count / 2 ? ctx->sm_count / 2 : n);
+    }
+    if (max_pairs == 0) return launch_tc<HD, FMT, ACT, false>(ctx, p);
+    const long long units = (long long)((p.ntiles + 1) / 2) * p.E;
+    const int pairs = units < max_pairs ? (int)units : max_pairs;
+    cfg.gridDim = dim3(2 * pairs);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // the fused rollout step: swish dynamics ensembles of any supported width
 template <int FMT>
 int launch_tc_fused(cmbpo_ctx* ctx, const TcParams& p, int hd) {
@@ -1053,6 +1107,12 @@ template <int FMT>
 int launch_tc_hd(cmbpo_ctx* ctx, const TcParams& p, int hd, int act) {
     if (hd == 128) return launch_tc_act<128, FMT>(ctx, p, act);
     if (hd == 256) return launch_tc_act<256, FMT>(ctx, p, act);
+#ifndef CMBPO_NO_PAIRS
+    if (p.ntiles >= 2) {
+        if (act == CMBPO_ACT_SWISH) return launch_tc_pairs<512, FMT, CMBPO_ACT_SWISH>(ctx, p);
+        return launch_tc_pairs<512, FMT, CMBPO_ACT_TANH>(ctx, p);
+    }
+#endif
     if (act == CMBPO_ACT_SWISH) return launch_tc<512, FMT, CMBPO_ACT_SWISH, false>(ctx, p);
     return launch_tc<512, FMT, CMBPO_ACT_TANH, false>(ctx, p);
 }
