@@ -112,3 +112,98 @@ def load_pe(engine, which, model_dir, name, timestep, elite_inds=None):
     elites = list(range(E)) if elite_inds is None else [int(i) for i in elite_inds]
     return B200PE(engine, which, ck["W"], ck["b"], ck["acts"], ck["probabilistic"], elites,
                   ck["mu_in"], ck["var_in"], ck["mu_out"], ck["var_out"], name=name)
+
+
+# ---- the policy's SavedModel (utilities/logx.py:202-259, policies/cpo_policy.py:890-894) ---------------------------
+_DENSE = re.compile(r"(?P<scope>.*/)?pi/dense(?:_(?P<i>\d+))?/(?P<kind>kernel|bias)")
+_FCVAR = re.compile(r"(?P<scope>.*/)?(?P<ens>[^/]+)/Layer(?P<i>\d+)/FC_(?P<kind>weights|biases)")
+
+
+class _Ens:
+    pass
+
+
+def read_policy_savedmodel(export_dir, vf_activation="swish", vf_elites=None):
+    """Variables of the SavedModel that `CPOPolicy.save` writes -> dict(actor_W, actor_b, log_std, v, vc).
+
+    The builder stores every global variable of the session under its graph name (no TensorFlow needed to read
+    them, see tf_bundle.py):
+      * the actor: `AC/pi/dense{,_1,_2}/{kernel,bias}` ([in,out] / [out], tanh hidden, linear output) and
+        `AC/pi/log_std` (network/ac_network.py:26-33, 99-123);
+      * the value ensembles `AC/VEnsemble/...`, `AC/VCEnsemble/...` (policies/cpo_policy.py:467-468): per layer
+        `Layer<i>/FC_weights` [E,in,out], `FC_biases` [E,1,out] (models/pens/fc.py:135-166), the scalers
+        `scaler_in_mu`, `scaler_in_std` (which holds the VARIANCE, pens/utils.py:112-114), `scaler_out_*`, and
+        `max_log_var` / `min_log_var` when trained with the NLL loss (pe.py:199-202).
+    Optimizer slots (`.../Adam`, `.../Adam_1`) are ignored.  The hidden activation and the elite list are
+    constructor arguments in the reference, not variables: pass them (`vf_activation`, `vf_elites`)."""
+    from .tf_bundle import read_bundle, read_index
+
+    prefix = os.path.join(export_dir, "variables", "variables")
+    entries, _ = read_index(prefix + ".index")
+    keys = ("scaler_in_mu", "scaler_in_std", "scaler_out_mu", "scaler_out_std", "max_log_var", "min_log_var")
+    wanted = [n for n in entries
+              if not n.endswith(("/Adam", "/Adam_1")) and (_DENSE.fullmatch(n) or n.endswith("pi/log_std") or
+                  (n.split("/")[-2:-1] in (["VEnsemble"], ["VCEnsemble"]) and n.split("/")[-1] in keys) or
+                  (_FCVAR.fullmatch(n) and _FCVAR.fullmatch(n).group("ens") in ("VEnsemble", "VCEnsemble")))]
+    tens = read_bundle(prefix, names=wanted)        # the dynamics model and optimizer slots of the same graph stay on disk
+    dense = {}
+    log_std = None
+    ens = {}
+    for name, a in tens.items():
+        if name.endswith("/Adam") or name.endswith("/Adam_1"):
+            continue
+        m = _DENSE.fullmatch(name)
+        if m:
+            dense.setdefault(int(m.group("i") or 0), {})[m.group("kind")] = a
+            continue
+        if name.endswith("pi/log_std"):
+            log_std = np.asarray(a, np.float32).reshape(-1)
+            continue
+        m = _FCVAR.fullmatch(name)
+        if m:
+            ens.setdefault(m.group("ens"), {}).setdefault("layers", {}).setdefault(int(m.group("i")), {})[m.group("kind")] = a
+            continue
+        for key in ("scaler_in_mu", "scaler_in_std", "scaler_out_mu", "scaler_out_std", "max_log_var", "min_log_var"):
+            if name.endswith("/" + key):
+                ens.setdefault(name.split("/")[-2], {})[key] = a
+    if not dense or log_std is None:
+        raise ValueError("%s holds no Gaussian MLP actor (pi/dense*/kernel, pi/log_std)" % export_dir)
+    idx = sorted(dense)
+    if idx != list(range(len(idx))) or any(set(dense[i]) != {"kernel", "bias"} for i in idx):
+        raise ValueError("%s: incomplete actor layers %s" % (export_dir, idx))
+    out = dict(actor_W=[np.asarray(dense[i]["kernel"], np.float32) for i in idx],
+               actor_b=[np.asarray(dense[i]["bias"], np.float32) for i in idx], log_std=log_std)
+    for key, ens_name in (("v", "VEnsemble"), ("vc", "VCEnsemble")):
+        e = ens.get(ens_name)
+        if e is None or "layers" not in e:
+            out[key] = None
+            continue
+        li = sorted(e["layers"])
+        if li != list(range(len(li))) or any(set(e["layers"][i]) != {"weights", "biases"} for i in li):
+            raise ValueError("%s: incomplete %s layers %s" % (export_dir, ens_name, li))
+        o = _Ens()
+        o.W = [np.ascontiguousarray(e["layers"][i]["weights"], np.float32) for i in li]
+        o.b = [np.ascontiguousarray(np.asarray(e["layers"][i]["biases"], np.float32).reshape(o.W[0].shape[0], -1)) for i in li]
+        o.acts = [vf_activation] * (len(li) - 1) + [None]
+        o.probabilistic = "max_log_var" in e
+        E = o.W[0].shape[0]
+        o.elite_inds = list(range(E)) if vf_elites is None else [int(i) for i in vf_elites]
+        for nm, src in (("mu_in", "scaler_in_mu"), ("var_in", "scaler_in_std"), ("mu_out", "scaler_out_mu"), ("var_out", "scaler_out_std")):
+            setattr(o, nm, np.asarray(e[src], np.float32).reshape(1, -1) if src in e else None)
+        o.max_logvar = e.get("max_log_var")
+        o.min_logvar = e.get("min_log_var")
+        out[key] = o
+    return out
+
+
+def load_policy(engine, export_dir, vf_activation="swish", vf_elites=None, seed=0):
+    """A `B200Policy` driven by the variables of the reference's policy SavedModel."""
+    from .policy import B200Policy
+
+    ck = read_policy_savedmodel(export_dir, vf_activation, vf_elites)
+    if ck["v"] is None or ck["vc"] is None:
+        raise ValueError("%s holds no VEnsemble / VCEnsemble variables" % export_dir)
+    pol = B200Policy(engine, seed=seed)
+    pol.load_actor(ck["actor_W"], ck["actor_b"], ck["log_std"])
+    pol.load_values(ck["v"], ck["vc"])
+    return pol
