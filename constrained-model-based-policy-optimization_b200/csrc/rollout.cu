@@ -39,55 +39,93 @@ struct PolicyRowsArgs {
     float *last_val, *last_cval;
 };
 
-constexpr int POLICY_ROWS = 128;      // rows (= threads) per block of policy_rows_kernel
+constexpr int POLICY_ROWS = 128;      // rows per block of policy_rows_kernel
+constexpr int POLICY_THREADS = 384;   // 128 row threads + 256 threads for the (row, four action dims) items
 
-// Phase 1, one thread per row: value heads, pending bootstraps, Gaussian head (pi, logp).  Phase 2,
-// all threads: the block's [128, O+A] slice of the dynamics input `xin` = concat(obs, pi) is one
-// contiguous range -> written with consecutive threads on consecutive floats (a per-row loop writes
-// 32 different 128-byte lines per store instruction).
+// Phase 1 runs two kinds of threads side by side (a row's work done by ONE thread is a ~50 k-cycle dependent
+// chain -- value-head loads, a Philox block and two Box-Muller pairs per four action dims, exp / divide per dim --
+// and 100 k rows are only ~5 warps per scheduler, so that version was bound by its own latency: 27 us per launch):
+//   threads [0,128)    one per row: value heads, pending bootstraps (model_sampler.py:401-407)
+//   threads [128,384)  one per (row, quad of action dims): the Gaussian head's noise, pi and log-density
+//                      terms of those dims (ac_network.py:105-111, 46-48), pi / mu written out
+// then the row thread adds the row's terms in numpy's order (the same additions in the same order as before:
+// bit-identical).  Phase 2, all threads: the block's [128, O+A] slice of the dynamics input `xin` = concat(obs, pi)
+// is one contiguous range -> written with consecutive threads on consecutive floats.
 template <bool FAST>
-__global__ void __launch_bounds__(POLICY_ROWS) policy_rows_kernel(PolicyRowsArgs a) {
+__global__ void __launch_bounds__(POLICY_THREADS) policy_rows_kernel(PolicyRowsArgs a) {
     __shared__ float s_pi[POLICY_ROWS * CMBPO_MAX_ACT];
+    __shared__ float s_term[POLICY_ROWS * CMBPO_MAX_ACT];
     __shared__ unsigned char s_live[POLICY_ROWS];
     const int64_t base = (int64_t)blockIdx.x * POLICY_ROWS;
-    const int64_t r = base + threadIdx.x;          // row of the (possibly compacted) batch
     const int64_t n_rows = a.n_dev ? *a.n_dev : a.N;
-    bool live = r < n_rows;
-    if (live) {
-        const int64_t p = a.row_path ? (int64_t)a.row_path[r] : r;   // path the per-path arrays are indexed by
-        const float v = value_of(a.v, a.N, r), vc = value_of(a.vc, a.N, r);
-        if (a.pending) {
-            uint8_t f = a.pending[p];
-            if (f) {                                   // model_sampler.py:401-407 on s_{t+1}
-                if (f & 1) a.last_val[p] = v;
-                if (f & 2) a.last_cval[p] = vc;
-                a.pending[p] = 0;
+    const int A = a.A;
+    if (threadIdx.x < POLICY_ROWS) {
+        const int64_t r = base + threadIdx.x;          // row of the (possibly compacted) batch
+        bool live = r < n_rows;
+        if (live) {
+            const int64_t p = a.row_path ? (int64_t)a.row_path[r] : r;   // path the per-path arrays are indexed by
+            const float v = value_of(a.v, a.N, r), vc = value_of(a.vc, a.N, r);
+            if (a.pending) {
+                uint8_t f = a.pending[p];
+                if (f) {                                   // model_sampler.py:401-407 on s_{t+1}
+                    if (f & 1) a.last_val[p] = v;
+                    if (f & 2) a.last_cval[p] = vc;
+                    a.pending[p] = 0;
+                }
+            }
+            live = !(a.alive && !a.alive[p]);
+            if (live) {
+                if (a.vout) a.vout[r] = v;
+                if (a.vcout) a.vcout[r] = vc;
+            }
+            live = live && a.mu_raw;
+        }
+        s_live[threadIdx.x] = live ? 1 : 0;
+    } else if (a.mu_raw) {
+        const int NQ = (A + 3) >> 2;
+        for (int it = threadIdx.x - POLICY_ROWS; it < POLICY_ROWS * NQ; it += POLICY_THREADS - POLICY_ROWS) {
+            const int rr = it / NQ, q = it - rr * NQ;
+            const int64_t r = base + rr;
+            if (r >= n_rows) continue;
+            const int64_t p = a.row_path ? (int64_t)a.row_path[r] : r;
+            if (a.alive && !a.alive[p]) continue;
+            const int64_t gid = a.path_ids ? (int64_t)a.path_ids[r] : a.path_base + p;
+            const int a0 = q * 4, na = (A - a0) < 4 ? (A - a0) : 4;
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            if (a.eps) {
+                for (int k = 0; k < na; ++k) z[k] = a.eps[p * A + a0 + k];
+            } else {                                   // one Philox block and two Box-Muller pairs per four values
+                uint32_t o[4];
+                philox4x32_10((uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)a.step,
+                              ((uint32_t)RNG_STREAM_ACT << 16) | (uint32_t)q, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), o);
+                box_muller(o[0], o[1], z[0], z[1]);
+                if (na > 2) box_muller(o[2], o[3], z[2], z[3]);
+            }
+            for (int k = 0; k < na; ++k) {
+                const int i = a0 + k;
+                const float mu = a.mu_raw[r * A + i];
+                float pi;
+                s_term[rr * A + i] = actor_dim<FAST>(mu, a.log_std[i], z[k], pi);
+                s_pi[rr * A + i] = pi;
+                if (a.pi) a.pi[r * A + i] = pi;
+                if (a.mu) a.mu[r * A + i] = mu;
             }
         }
-        live = !(a.alive && !a.alive[p]);
-        if (live) {
-            if (a.vout) a.vout[r] = v;
-            if (a.vcout) a.vcout[r] = vc;
-        }
-        live = live && a.mu_raw;
-        if (live) {
-            const int64_t gid = a.path_ids ? (int64_t)a.path_ids[r] : a.path_base + p;
-            const float lp = policy_head_row<FAST>(a.mu_raw + r * a.A, a.log_std, a.eps ? a.eps + p * a.A : nullptr,
-                                                   a.seed, gid, a.step, a.A, a.pi ? a.pi + r * a.A : nullptr,
-                                                   a.mu ? a.mu + r * a.A : nullptr, s_pi + threadIdx.x * a.A);
-            if (a.logp) a.logp[r] = lp;
-        }
     }
-    s_live[threadIdx.x] = live ? 1 : 0;
-    if (!a.xin) return;                             // uniform over the block
     __syncthreads();
-    const int W = a.O + a.A;
+    if (threadIdx.x < POLICY_ROWS && s_live[threadIdx.x] && a.logp) {
+        NpSumStream acc(A);
+        for (int i = 0; i < A; ++i) acc.add(i, s_term[threadIdx.x * A + i]);
+        a.logp[base + threadIdx.x] = acc.result();
+    }
+    if (!a.xin) return;                             // uniform over the block
+    const int W = a.O + A;
     const int64_t left = n_rows - base;
     const int64_t nrows = left < 0 ? 0 : (left < POLICY_ROWS ? left : POLICY_ROWS);
-    for (int idx = threadIdx.x; idx < nrows * W; idx += POLICY_ROWS) {
+    for (int idx = threadIdx.x; idx < nrows * W; idx += POLICY_THREADS) {
         const int rr = idx / W, c = idx - rr * W;
         if (!s_live[rr]) continue;
-        a.xin[base * W + idx] = c < a.O ? a.obs[(base + rr) * a.O + c] : s_pi[rr * a.A + (c - a.O)];
+        a.xin[base * W + idx] = c < a.O ? a.obs[(base + rr) * a.O + c] : s_pi[rr * A + (c - a.O)];
     }
 }
 
@@ -429,7 +467,7 @@ int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precis
         a.log_std = ctx->log_std;
         a.v = make_head(v, raw + (size_t)a.N * A); a.v.ld = A;
         a.vc = make_head(vc, raw + (size_t)(1 + v.E) * a.N * A); a.vc.ld = A;
-        policy_rows_kernel<true><<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
+        policy_rows_kernel<true><<<cdiv(a.N, POLICY_ROWS), POLICY_THREADS, 0, ctx->stream>>>(a);
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -450,8 +488,8 @@ int policy_forward(cmbpo_ctx* ctx, PolicyRowsArgs a, bool with_actor, int precis
     }
     a.mu_raw = raw_mu; a.log_std = ctx->log_std;
     a.v = make_head(v, raw_v); a.vc = make_head(vc, raw_vc);
-    if (precision != CMBPO_PREC_FP32) policy_rows_kernel<true><<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
-    else policy_rows_kernel<false><<<cdiv(a.N, POLICY_ROWS), POLICY_ROWS, 0, ctx->stream>>>(a);
+    if (precision != CMBPO_PREC_FP32) policy_rows_kernel<true><<<cdiv(a.N, POLICY_ROWS), POLICY_THREADS, 0, ctx->stream>>>(a);
+    else policy_rows_kernel<false><<<cdiv(a.N, POLICY_ROWS), POLICY_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
