@@ -547,6 +547,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
         unsigned long long c_w = 0, c_d = 0, c_h1 = 0, c_x = 0;
         const long long t_begin = DBG ? clock64() : 0;
         auto next_stage = [&]() { if (++s == NSM) { s = 0; ph ^= 1; } };
+#ifndef CMBPO_NO_SPLIT_ISSUE
+        // SPLIT (single-thread issuer, 4-tile stages): the issuing thread's bookkeeping between two batches of MMAs
+        // (a try_wait costs ~60 cycles even when the phase completed long ago) is not covered by queued MMAs -- the
+        // layer-1 phase ran at ~44 cycles per MMA with all-zero operands too, i.e. not a power or data effect.  So
+        // every wait is issued in the MIDDLE of a batch (after its first 8 MMAs): the W_FULL wait of the NEXT stage
+        // and the hoisted accumulator hand-off; at a batch boundary only the commits remain.
+        constexpr bool SPLIT = SINGLE && TPS == 4;
+#else
+        constexpr bool SPLIT = false;
+#endif
+        // stages this CTA consumes in total (the W_FULL wait runs one stage ahead only while a next stage exists)
+        const uint32_t total_stages = (uint32_t)(u1 - u0) * (uint32_t)(NC / G0 + NHID * NC * (KP / TPS));
+        uint32_t q_stage = 0;
+        uint32_t pre_n = 0;                 // upcoming ring stages whose W_FULL phase was already seen complete
+        // C8 (512-wide ordinary members): a whole layer-1 chunk (2 stages, 32 MMAs) per asm statement with the next
+        // chunk's barrier tests embedded (mma_f16_ts_chunk8, tc_common.cuh)
+        // (measured 10 % SLOWER than two half-stage batches per stage -- 0.436 vs 0.394 ms -- and kept for reference only)
+#ifdef CMBPO_C8
+        constexpr bool C8 = SPLIT && !DBG && (KP / TPS == 2);
+#else
+        constexpr bool C8 = false;
+#endif
+        const uint32_t bar_a1 = smem_u32(bar);
         if (!SINGLE || elect_one()) {
         int cur_tile = -1;
         for (int u = u0; u < u1; ++u) {
@@ -559,7 +582,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
             }
             {
                 for (int j0 = 0; j0 < NC; j0 += G0) {       // layer 0: D = XA x W0 chunk (G0 chunks per stage)
-                    wait_t<DBG>(bar + W_FULL + s, ph, c_w);
+                    if (pre_n) --pre_n; else wait_t<DBG>(bar + W_FULL + s, ph, c_w);
+                    ++q_stage;
 #pragma unroll
                     for (int jj = 0; jj < G0; ++jj) {
                         // one chunk per instruction, buffer = chunk parity: the two epilogue pairs run as
@@ -602,15 +626,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) ens_mlp3_tc_kernel(const TcParams
                         tc_fence_after();
                     }
                     TRACE(0, 300 + j);
-                    for (int kq = 0; kq < KP / TPS; ++kq) {
-                        wait_t<DBG>(bar + W_FULL + s, ph, c_w);      // TMA completion: no tcgen05 fence needed
-                        if (HOIST && kq == KP / TPS - 1 && j + 1 < NC) {
-                            const uint32_t g1 = g + 1;
-                            wait_t<DBG>(bar + D_EMPTY + (g1 & 1), ((g1 >> 1) & 1) ^ 1, c_d);
-                            tc_fence_after();
+                    if (C8) {
+                        const uint32_t s0 = s, ph0 = ph;
+                        next_stage();
+                        const uint32_t s1 = s, ph1 = ph;
+                        next_stage();                                   // (s, ph): the first stage after this chunk
+                        if (pre_n) --pre_n; else mbar_wait_a(bar_a1 + 8 * (W_FULL + s0), ph0);
+                        if (pre_n) --pre_n; else mbar_wait_a(bar_a1 + 8 * (W_FULL + s1), ph1);
+                        q_stage += 2;
+                        const uint32_t ns1 = (s + 1 == NSM) ? 0u : s + 1, nph1 = (s + 1 == NSM) ? (ph ^ 1u) : ph;
+                        const uint32_t g1 = g + 1;
+                        const uint32_t flags = (q_stage < total_stages ? 1u : 0u) | (q_stage + 1 < total_stages ? 2u : 0u) |
+                                               (j + 1 < NC ? 4u : 0u);
+                        const uint32_t w0a = bar_a1 + 8 * (W_FULL + s), w1a = bar_a1 + 8 * (W_FULL + ns1);
+                        const uint32_t dea = bar_a1 + 8 * (D_EMPTY + (g1 & 1)), dep = ((g1 >> 1) & 1) ^ 1;
+                        const uint32_t ok = mma_f16_ts_chunk8<CL == 2>(tmem + COL_D + buf * 64, tmem_rt + col_a,
+                                                              dW0 + (uint64_t)((s0 * STAGE) >> 4), dW0 + (uint64_t)((s1 * STAGE) >> 4),
+                                                              idesc_h, 0u, w0a, ph, w1a, nph1, dea, dep, flags,
+                                                              bar_a1 + 8 * (W_EMPTY + s0));
+                        if (!ok) {                                      // rare: something the next chunk needs is not there yet
+                            if (flags & 1u) mbar_wait_a(w0a, ph);
+                            if (flags & 2u) mbar_wait_a(w1a, nph1);
+                            if (flags & 4u) mbar_wait_a(dea, dep);
                         }
+                        if (flags & 4u) tc_fence_after();
+                        pre_n = (flags & 1u) + ((flags >> 1) & 1u);
+                        if (CL == 2) mma_commit_mc_a(bar_a1 + 8 * (W_EMPTY + s1), 3);      // (the first stage was released inside)
+                        else mma_commit_a(bar_a1 + 8 * (W_EMPTY + s1));
+                        mma_commit_a(bar_a1 + 8 * (D_FULL + buf));
+                    } else
+                    for (int kq = 0; kq < KP / TPS; ++kq) {
+                        if (pre_n) --pre_n; else wait_t<DBG>(bar + W_FULL + s, ph, c_w);      // TMA completion: no tcgen05 fence needed
+                        ++q_stage;
+                        auto mid_waits = [&]() {
+                            if (SPLIT && q_stage < total_stages) {       // the NEXT stage's weights
+                                const uint32_t ns = (s + 1 == NSM) ? 0u : s + 1, nph = (s + 1 == NSM) ? (ph ^ 1u) : ph;
+                                wait_t<DBG>(bar + W_FULL + ns, nph, c_w);
+                                pre_n = 1;
+                            }
+                            if (HOIST && kq == KP / TPS - 1 && j + 1 < NC) {
+                                const uint32_t g1 = g + 1;
+                                wait_t<DBG>(bar + D_EMPTY + (g1 & 1), ((g1 >> 1) & 1) ^ 1, c_d);
+                                tc_fence_after();
+                            }
+                        };
+                        if (!SPLIT) mid_waits();
                         if (SINGLE || elect_one()) {
                             // TPS tiles x 4 K-steps from one asm statement (addresses chained inside, see tc_common.cuh)
+                            if (SPLIT) {
+                                const uint32_t a0 = tmem_rt + col_a + ((j / CPM) * KP + kq * TPS) * 32;
+                                const uint64_t b0 = dW0 + (uint64_t)((s * STAGE) >> 4);
+#ifdef CMBPO_SPLIT4
+                                mma_f16_ts_tiles<1>(tmem + COL_D + buf * 64, a0, b0, idesc_h, kq > 0);
+                                mid_waits();
+                                mma_f16_ts_tiles<1>(tmem + COL_D + buf * 64, a0 + 32, b0 + (uint64_t)((1 * TILE) >> 4), idesc_h, 1u);
+                                mma_f16_ts_tiles<1>(tmem + COL_D + buf * 64, a0 + 64, b0 + (uint64_t)((2 * TILE) >> 4), idesc_h, 1u);
+                                mma_f16_ts_tiles<1>(tmem + COL_D + buf * 64, a0 + 96, b0 + (uint64_t)((3 * TILE) >> 4), idesc_h, 1u);
+#else
+                                mma_f16_ts_tiles<2>(tmem + COL_D + buf * 64, a0, b0, idesc_h, kq > 0);
+                                mid_waits();
+                                mma_f16_ts_tiles<2>(tmem + COL_D + buf * 64, a0 + 64, b0 + (uint64_t)((2 * TILE) >> 4), idesc_h, 1u);
+#endif
+                            } else
                             mma_f16_ts_tiles<TPS>(tmem + COL_D + buf * 64, tmem_rt + col_a + ((j / CPM) * KP + kq * TPS) * 32,
                                                   dW0 + (uint64_t)((s * STAGE) >> 4), idesc_h, kq > 0);
                             if (CL == 2) mma_commit_mc(bar + W_EMPTY + s, 3); else mma_commit(bar + W_EMPTY + s);
@@ -1060,6 +1137,8 @@ int launch_tc_pairs(cmbpo_ctx* ctx, const TcParams& p) {
         int n = 0;
         CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
         max_pairs = n < 1 ? 0 : (n > ctx->sm_count / 2 ? ctx->sm_count / 2 : n);
+        // pairs are worth ~2 %; a part whose GPC layout leaves more than two SMs without a partner loses more than that
+        if (2 * max_pairs < ctx->sm_count - 2) max_pairs = 0;
     }
     if (max_pairs == 0) return launch_tc<HD, FMT, ACT, false>(ctx, p);
     const long long units = (long long)((p.ntiles + 1) / 2) * p.E;

@@ -8,7 +8,7 @@ t = sys.argv[1]
 try:
     d = json.load(open("gpurun_out/ab_%s.json" % t))
     b = d["breakdown_ms_per_step"]
-    print("%-10s value %.2fM  ms/step %.3f  K1 %.4f ms  dyn %.2f pol %.2f row %.2f" % (t, d["value"] / 1e6, d["ms_per_step"], d["roofline"]["launch_ms"], b["dynamics_gemm_chain"], b["policy_pass"], b["row_kernel"]))
+    print("%-10s value %.2fM  ms/step %.3f  K1 %.4f ms  dyn %.2f pol %.2f row %.2f  gae %.3f of HBM" % (t, d["value"] / 1e6, d["ms_per_step"], d["roofline"]["launch_ms"], b["dynamics_gemm_chain"], b["policy_pass"], b["row_kernel"], d["gae"]["frac"]))
 except Exception as e:
     print(t, "no result", e)
 PY

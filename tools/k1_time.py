@@ -13,6 +13,9 @@ H = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 O = int(sys.argv[3]) if len(sys.argv) > 3 else 17
 A = int(sys.argv[4]) if len(sys.argv) > 4 else 6
 dyn, actor, v, vc = orc.make_problem(0, O, A, hidden=(H, H))
+if os.environ.get("K1_ZERO"):      # data-dependence probe: all-zero weights and biases (same instruction stream)
+    for w in dyn.W: w[...] = 0
+    for b in dyn.b: b[...] = 0
 eng = cb.Engine(0, precision="fp16")
 model = cb.B200PE.from_arrays(eng, L.NET_DYN, dyn)
 obs, act = orc.make_states(1, N, O, A, dyn)
