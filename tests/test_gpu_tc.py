@@ -41,6 +41,28 @@ def test_predict_ensemble_tc(engine, key, prec, vtol):
         assert np.allclose(g, w, rtol=tol * scale, atol=tol * scale), k
 
 
+@pytest.mark.parametrize("N", [127, 129, 256, 257, 385, 128 * 149 + 5])
+def test_cluster_pair_tile_counts(engine, N):
+    """The cluster-pair kernel (two CTAs stream one copy of the weights, ens_tc.cu CL = 2) against the oracle for
+    row counts around its edge cases: one tile (pairs not used), exactly one pair, an odd tile count (the last
+    pair's second CTA runs the protocol on a tile without rows), more pairs than the GPU holds."""
+    task, O, A = TASKS["hcs"]
+    dyn, actor, v, vc = orc.make_problem(83, O, A, hidden=(512, 512), task=task)
+    model, policy = load_problem(engine, dyn, actor, v, vc)
+    obs, act = orc.make_states(84, N, O, A, dyn)
+    x = np.concatenate([obs, act], -1)
+    mean, var = (t.cpu().numpy() for t in model.predict_ensemble_device(x, precision="fp16"))
+    wm, wv = orc.pe_forward(dyn, x)
+    sig = np.maximum(np.sqrt(dyn.var_out), 1e-2)
+    assert mean.shape == wm.shape and np.isfinite(mean).all()
+    assert _err(mean, wm, sig) <= 1.0
+    assert float(np.max(np.abs(var - wv) / wv)) <= 1e-3
+    # row r depends on row r only: the same rows inside a larger batch give the same bits
+    if N >= 257:
+        m2, v2 = (t.cpu().numpy() for t in model.predict_ensemble_device(x[:200], precision="fp16"))
+        assert np.array_equal(m2, mean[:, :200]) and np.array_equal(v2, var[:, :200])
+
+
 def test_rollout_fp16_vs_fp32(engine):
     """H-step: the tcgen05 rollout tracks the fp32 rollout; stated per-step tolerance 2e-3*(t+1)
     relative to the state scale, lengths equal except near-threshold flips (< 2%)."""
