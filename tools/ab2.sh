@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_soak.py -m gpu -x -q 2>&1 | tail -3
-bash tools/ab.sh noc8 default noc8 default
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+bash tools/ab.sh base default base default
