@@ -271,7 +271,7 @@ __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, unsigned 
 template <int FMT, int ACT>
 __device__ __forceinline__ void drain32(uint32_t d_addr, const float* bias, uint32_t dst_addr,
                                         uint32_t d_empty, uint32_t dst_free, uint32_t dst_parity,
-                                        uint32_t* tr = nullptr) {
+                                        uint32_t* tr = nullptr, bool rt_swish = false) {
     uint32_t r[32];
     tmem_ld32(d_addr, r);
     tmem_ld_wait();
@@ -293,7 +293,15 @@ __device__ __forceinline__ void drain32(uint32_t d_addr, const float* bias, uint
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (ACT == CMBPO_ACT_SWISH) ? swish_half(v[i]) : tanh_approx(v[i]);
+    for (int i = 0; i < 32; ++i) {
+        if (ACT == 0) {          // per-member run-time activation, ONE copy of the code: both forms from one MUFU, then a select
+            const float r = tanh_approx(v[i]);
+            const float sw = fmaf(v[i], r, v[i]);
+            v[i] = rt_swish ? sw : r;
+        } else {
+            v[i] = (ACT == CMBPO_ACT_SWISH) ? swish_half(v[i]) : tanh_approx(v[i]);
+        }
+    }
 #pragma unroll
     for (int c = 0; c < 16; ++c) q[c] = Cvt<FMT>::pack(v[2 * c], v[2 * c + 1]);
     if (tr) tr[1] = (uint32_t)clock64();
@@ -309,6 +317,9 @@ template <int FMT, int ACT>
 __device__ __forceinline__ void drain32_act(int act_rt, uint32_t d_addr, const float* bias, uint32_t dst_addr,
                                             uint32_t d_empty, uint32_t dst_free, uint32_t dst_parity,
                                             uint32_t* tr = nullptr) {
+#ifndef CMBPO_TWO_DRAIN_COPIES
+    if (ACT == 0) { drain32<FMT, 0>(d_addr, bias, dst_addr, d_empty, dst_free, dst_parity, nullptr, act_rt != CMBPO_ACT_TANH); return; }
+#endif
     if (ACT != 0) {
         drain32<FMT, ACT>(d_addr, bias, dst_addr, d_empty, dst_free, dst_parity, tr);
     } else if (act_rt == CMBPO_ACT_TANH) {
