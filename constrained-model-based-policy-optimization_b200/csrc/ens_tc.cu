@@ -21,7 +21,9 @@
 // TMEM allocator + layer-2 MMA issuer, warp 3 = layer-2 weight producer (setmaxnreg 32), warps 4-19 =
 // four epilogue warpgroups (setmaxnreg 112; thread <-> row <-> TMEM lane; a pair of warpgroups owns
 // one accumulator buffer, each warpgroup 32 of the chunk's 64 columns).  Work unit = (row tile,
-// member), or (row tile, group of 4 narrow members) in grouped mode.
+// member), or (row tile, group of 4 narrow members) in grouped mode.  Wide ordinary ensembles run as CLUSTER PAIRS
+// (template parameter CL = 2): two CTAs work on the same member and multicast one copy of its weights into both
+// rings (see the comment at the kernel).
 //
 // Replaces models/pens/fc.py:74-95 x3 + the input scaler of models/pens/utils.py:156 (fused into the
 // XA load).  The output scaler / exp are applied by the consumer (ens_head_kernel or the rollout row
