@@ -1148,7 +1148,10 @@ int launch_tc_pairs(cmbpo_ctx* ctx, const TcParams& p) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         cfg.gridDim = dim3(2 * (ctx->sm_count / 2));
         int n = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {      // no cluster support here: ordinary launch
+            (void)cudaGetLastError();
+            n = 0;
+        }
         max_pairs = n < 1 ? 0 : (n > ctx->sm_count / 2 ? ctx->sm_count / 2 : n);
         // pairs are worth ~2 %; a part whose GPC layout leaves more than two SMs without a partner loses more than that
         if (2 * max_pairs < ctx->sm_count - 2) max_pairs = 0;
