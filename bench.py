@@ -289,6 +289,78 @@ def cpu_gae_ms_per_1m():
     return (time.perf_counter() - t0) * 1e3 / (B * T / 1e6)
 
 
+def cpu_gae_reference_ms_per_1m():
+    """the reference's GAE arithmetic on the host -- `np.append`, deltas, flip /
+    `scipy.signal.lfilter([1],[1,-d])` / flip (utilities/utils.py:186-188 as called by modelbuffer.py:163-179), float64
+    output stored into float32 buffers -- over 1 M steps as [32768 paths x 32 steps] and as one flat CPOBuffer of
+    1049 paths x 1000 steps (one `finish_path` per path, cpobuffer.py:179-207).  scipy is single threaded."""
+    import scipy.signal
+    rng = np.random.default_rng(0)
+
+    def gae(r, v, c, cv, lv, lc):
+        out = []
+        for x, val, last, g, lam in ((r, v, lv, 0.99, 0.95), (c, cv, lc, 0.97, 0.5)):
+            vals = np.append(val, last, axis=-1)
+            deltas = x + g * vals[..., 1:] - vals[..., :-1]
+            flipped = np.flip(deltas, axis=-1)
+            adv = np.flip(scipy.signal.lfilter([1], [1, float(-g * lam)], flipped, axis=-1), axis=-1).astype(np.float32)
+            out += [adv, (adv + val).astype(np.float32)]
+        return out
+
+    B, T = 32768, 32
+    r, v, c, cv = (rng.standard_normal((B, T)).astype(np.float32) for _ in range(4))
+    lv, lc = (rng.standard_normal((B, 1)).astype(np.float32) for _ in range(2))
+    gae(r[:64], v[:64], c[:64], cv[:64], lv[:64], lc[:64])
+    t0 = time.perf_counter()
+    gae(r, v, c, cv, lv, lc)
+    batched = (time.perf_counter() - t0) * 1e3 / (B * T / 1e6)
+    P, L_ = 1049, 1000
+    r, v, c, cv = (rng.standard_normal(P * L_).astype(np.float32) for _ in range(4))
+    t0 = time.perf_counter()
+    for i in range(P):
+        sl = slice(i * L_, (i + 1) * L_)
+        gae(r[sl], v[sl], c[sl], cv[sl], np.zeros(1, np.float32), np.zeros(1, np.float32))
+    flat = (time.perf_counter() - t0) * 1e3 / (P * L_ / 1e6)
+    return {"paths_32768x32_ms_per_1M_steps": batched, "flat_1049x1000_ms_per_1M_steps": flat,
+            "what": "BASELINE.md B4: scipy.signal.lfilter GAE + cost-GAE exactly as the reference calls it, one host thread"}
+
+
+def cpu_single_step_torch(n_rows, seed=0):
+    """the same single FakeEnv.step with the three ensemble GEMMs through torch-CPU `bmm` (MKL, all
+    threads) instead of numpy; the head / KL / statics arithmetic stays the oracle port's.  rows per second."""
+    import torch
+    from oracle import cmbpo_oracle as orc
+    dyn, actor, v, vc = orc.make_problem(seed, OBS, ACT, hidden=HIDDEN, task=TASK)
+    obs, act = orc.make_states(seed + 1, n_rows, OBS, ACT, dyn)
+    W = [torch.from_numpy(np.ascontiguousarray(w)) for w in dyn.W]
+    bs = [torch.from_numpy(np.ascontiguousarray(np.asarray(b).reshape(w.shape[0], 1, -1))) for w, b in zip(dyn.W, dyn.b)]
+    sig_in = torch.from_numpy(np.maximum(np.sqrt(dyn.var_in), 1e-2).astype(np.float32))
+    mu_in = torch.from_numpy(np.asarray(dyn.mu_in, np.float32))
+
+    def forward(x):
+        h = ((torch.from_numpy(x) - mu_in) / sig_in).unsqueeze(0).expand(W[0].shape[0], -1, -1)
+        for i, (w, b) in enumerate(zip(W, bs)):
+            h = torch.baddbmm(b, h, w)
+            if i < len(W) - 1:
+                h = h * torch.sigmoid(h)
+        return h.numpy()
+
+    x = np.concatenate([obs, act], -1).astype(np.float32)
+    forward(x[:256])
+    t0 = time.perf_counter()
+    raw = forward(x)
+    D = raw.shape[-1] // 2
+    sig_o = np.maximum(np.sqrt(dyn.var_out), 1e-2).astype(np.float32)
+    mean = raw[..., :D] * sig_o + dyn.mu_out
+    var = np.exp(raw[..., D:] + 2 * np.log(sig_o))
+    std = np.sqrt(var)
+    orc.average_dkl(mean[..., :OBS], std[..., :OBS]).mean(-1)
+    np.var(mean[..., :OBS], axis=0)
+    orc.hcs_cost(mean[0, :, :OBS] + obs)
+    dt = time.perf_counter() - t0
+    return n_rows / dt, dt, int(torch.get_num_threads())
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -313,7 +385,7 @@ def run_reference(args, rank, world):
                    "act": ACT, "ensemble": "7x(512,512) swish, 5 elites"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d start states x %d steps per pass, %d passes" % (B, MAXROLL - 1, args.steps),
-                         "gae_ms_per_1M_steps": cpu_gae_ms_per_1m()},
+                         "gae_ms_per_1M_steps": cpu_gae_ms_per_1m(), "gae": cpu_gae_reference_ms_per_1m()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -661,11 +733,15 @@ def bench_hcs(rig, args, cfg):
             cpu_n, cpu_dt = cpu_rollout_sample(scaled)
             args.cpu_batch = scaled
         rows_s, rows_dt = cpu_single_step(10000)
+        trows_s, trows_dt, tthreads = cpu_single_step_torch(10000)
         cpu = {"value": cpu_n / cpu_dt, "unit": UNIT, "cores": host_threads(), "kind": "port",
                "sample": "%d start states x %d steps (one pass, %.1f s)" % (args.cpu_batch, T - 1, cpu_dt),
                "single_step": {"rows_per_s": rows_s, "rows": 10000, "seconds": rows_dt,
-                               "what": "BASELINE configs[0]: one FakeEnv.step (predict_ensemble + KL + statics) on 10k "
-                                       "(obs17, act6) rows, oracle port"}}
+                               "what": "BASELINE configs[0] / BASELINE.md B1: one FakeEnv.step (predict_ensemble + KL + "
+                                       "statics) on 10k (obs17, act6) rows, oracle port (numpy)"},
+               "single_step_torch_bmm": {"rows_per_s": trows_s, "rows": 10000, "seconds": trows_dt, "threads": tthreads,
+                                         "what": "BASELINE.md B2: the same step with the ensemble GEMMs through torch-CPU bmm"},
+               "gae": cpu_gae_reference_ms_per_1m()}
     line = base_line(rig, args, cfg, n_tr / (ms * 1e-3), ms / args.steps, {
         "start_states_per_gpu": B,
         "l2": "rollout buffers (%.0f MB/GPU) exceed the 126 MB L2; no explicit flush" %
