@@ -250,6 +250,7 @@ class ClockSampler:
 def cpu_rollout_sample(B, seed=0):
     """One reference-port pass (reset -> sample x 34 -> finish_all_paths -> get) on B start states."""
     from oracle import cmbpo_oracle as orc
+    orc.FAST_GEMM = True      # the member contraction as one multi-threaded BLAS GEMM (timing legs only)
     dyn, actor, v, vc = orc.make_problem(seed, OBS, ACT, hidden=HIDDEN, task=TASK)
     obs, _ = orc.make_states(seed + 1, B, OBS, ACT, dyn)
     noise = orc.TableNoise(seed + 2, MAXROLL, B, ACT, len(dyn.elite_inds))
@@ -265,6 +266,7 @@ def cpu_single_step(n_rows, seed=0):
     """BASELINE configs[0]: one FakeEnv.step (predict_ensemble + average_dkl + statics) on n_rows synthetic
     (obs17, act6) rows through the oracle port; rows per second."""
     from oracle import cmbpo_oracle as orc
+    orc.FAST_GEMM = True      # the member contraction as one multi-threaded BLAS GEMM (timing legs only)
     dyn, actor, v, vc = orc.make_problem(seed, OBS, ACT, hidden=HIDDEN, task=TASK)
     obs, act = orc.make_states(seed + 1, n_rows, OBS, ACT, dyn)
     noise = orc.TableNoise(seed + 2, 2, n_rows, ACT, len(dyn.elite_inds))
@@ -280,6 +282,7 @@ def cpu_single_step(n_rows, seed=0):
 
 def cpu_gae_ms_per_1m():
     from oracle import cmbpo_oracle as orc
+    orc.FAST_GEMM = True      # the member contraction as one multi-threaded BLAS GEMM (timing legs only)
     rng = np.random.default_rng(0)
     B, T = 8192, 34
     r, v, c, cv = (rng.standard_normal((B, T)).astype(np.float32) for _ in range(4))
@@ -330,6 +333,7 @@ def cpu_single_step_torch(n_rows, seed=0):
     threads) instead of numpy; the head / KL / statics arithmetic stays the oracle port's.  rows per second."""
     import torch
     from oracle import cmbpo_oracle as orc
+    orc.FAST_GEMM = True      # the member contraction as one multi-threaded BLAS GEMM (timing legs only)
     dyn, actor, v, vc = orc.make_problem(seed, OBS, ACT, hidden=HIDDEN, task=TASK)
     obs, act = orc.make_states(seed + 1, n_rows, OBS, ACT, dyn)
     W = [torch.from_numpy(np.ascontiguousarray(w)) for w in dyn.W]
@@ -380,7 +384,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "impl_note": "CPU port of the reference (numpy restatement of the TF "
-                               "graphs; TF 1.14 is not installable), bounded sample of the workload per step",
+                               "graphs; TF 1.14 is not installable; ensemble contractions as multi-threaded BLAS GEMMs), bounded sample of the workload per step",
                    "start_states_per_step": B, "maxroll": MAXROLL, "stored_steps": MAXROLL - 1, "obs": OBS,
                    "act": ACT, "ensemble": "7x(512,512) swish, 5 elites"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
