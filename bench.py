@@ -44,6 +44,11 @@ CONFIGS = {
     "ant1m": dict(task="ant", scaling="strong", total=1000000,
                   workload="BASELINE configs[2]: AntSafe ensemble rollout, 1M start states sharded over the ranks "
                            "(termination function shortens paths; alive-row compaction) + GAE/cost-GAE + normalisation"),
+    "hcs_unc": dict(task="hcs", scaling="weak", total_per_gpu=100000,
+                    workload="HalfCheetahSafe H-step rollout in the reference's DEFAULT rollout_mode 'uncertainty' "
+                             "(configs/cmbpo_hcs.py:28): a path is cut when its cumulative ensemble KL reaches dkl_lim = "
+                             "rollout_schedule[2] (= 5) x the mean one-step KL of 5000 start states (cmbpo.py:198-200); "
+                             "alive-row compaction; + GAE/cost-GAE + normalisation"),
     "hs_gae": dict(task="hum", scaling="weak",
                    workload="BASELINE configs[3]: HumanoidSafe (configs/cmbpo_hs) rollout feeding the GAE + cost-GAE "
                             "reverse scans; standalone GAE layouts in `gae_layouts`"),
@@ -414,6 +419,7 @@ class Rig:
         self.task, self.O, self.A = TASKS[task_key]
         self.dev = torch.device("cuda", local_rank)
         self.eng = cb.Engine(local_rank, precision=args.precision)
+        self.unc_mode, self.dkl_lim = False, 0.0
         self.dyn, self.actor, self.v, self.vc = wl.make_problem(0, self.O, self.A, hidden=HIDDEN, task=self.task)
         dev = self.dev
 
@@ -479,7 +485,7 @@ class Rig:
         def hot_path(step):
             bufs.start_obs = start
             bufs.run(self.env_cfg, seed=seed0 + step, path_id_base=path_base, precision=self.args.precision,
-                     flags=(L.ROLLOUT_FUSE if self.args.fuse else 0))
+                     flags=(L.ROLLOUT_FUSE if self.args.fuse else 0), uncertainty_mode=self.unc_mode, dkl_lim=self.dkl_lim)
             bufs.gae(GAE["gamma"], GAE["lam"], GAE["cost_gamma"], GAE["cost_lam"])
             sums = eng.adv_statistics_device(bufs.adv, bufs.cadv, bufs.ret, bufs.cret, B, T, 1, B, bufs.length,
                                              self.reduce_fn if world > 1 else None)
@@ -547,7 +553,7 @@ def dtype_name(precision):
 
 def mode_name(args):
     return ("injected-noise (mean + std*eps, Philox eps)" if args.mode == "injected" else "deterministic-mean") + \
-        ", Philox action noise / elite draws, dkl_lim=inf"
+        ", Philox action noise / elite draws, " + ("uncertainty cut-off (see workload)" if args.config == "hcs_unc" else "dkl_lim=inf")
 
 
 def run_cuda(args, rank, world, local_rank):
@@ -560,7 +566,8 @@ def run_cuda(args, rank, world, local_rank):
     cfg = CONFIGS[args.config]
     rig = Rig(cfg["task"], args, rank, world, local_rank)
     try:
-        {"hcs": bench_hcs, "ant1m": bench_ant1m, "hs_gae": bench_hs_gae, "sweep": bench_sweep}[args.config](rig, args, cfg)
+        {"hcs": bench_hcs, "ant1m": bench_ant1m, "hs_gae": bench_hs_gae, "sweep": bench_sweep,
+         "hcs_unc": bench_hcs_unc}[args.config](rig, args, cfg)
     finally:
         if world > 1:
             dist.destroy_process_group()
@@ -784,6 +791,15 @@ def bench_hcs(rig, args, cfg):
 
 
 # ---- configs[2]: AntSafe, 1M start states sharded (strong scaling) -----------------------------------
+def bench_hcs_unc(rig, args, cfg):
+    """The reference's default rollout mode: the limit is calibrated like cmbpo.py:198-200 (depth x mean one-step KL)."""
+    obs, act = rig.wl.make_states(7, 5000, rig.O, rig.A, rig.dyn)
+    out = rig.eng.fakeenv_step(rig.env_cfg, obs, act, seed=1, step=0)
+    rig.unc_mode, rig.dkl_lim = True, 5.0 * float(out["dkl_path"].mean())
+    cfg = dict(cfg, total=cfg["total_per_gpu"] * rig.world)
+    bench_ant1m(rig, args, cfg)
+
+
 def bench_ant1m(rig, args, cfg):
     world = rig.world
     total = args.total if args.total > 0 else cfg["total"]
