@@ -62,6 +62,21 @@ class Engine:
                 x = x.to(dtype)
             return x.contiguous()
         arr = np.ascontiguousarray(a)
+        if arr.nbytes >= (1 << 20) and arr.dtype == np.float32 and (dtype is None or dtype == t.float32):
+            # large pageable arrays (the start states of a rollout): one host copy into a cached page-locked block and
+            # one DMA, instead of the driver's chunked bounce-buffer path for pageable memory (~3x slower)
+            stage = getattr(self, "_h2d_stage", None)
+            if stage is None or stage.numel() < arr.size:
+                stage = self._h2d_stage = t.empty(arr.size, dtype=t.float32, pin_memory=True)
+                self._h2d_done = None
+            if self._h2d_done is not None:
+                self._h2d_done.synchronize()           # the previous upload out of this block has finished
+            view = stage[:arr.size].view(arr.shape)
+            view.copy_(t.from_numpy(arr))
+            x = view.to(self.device, non_blocking=True)
+            self._h2d_done = t.cuda.Event()
+            self._h2d_done.record()
+            return x
         x = t.from_numpy(arr).to(self.device, non_blocking=False)
         if dtype is not None:
             x = x.to(dtype)
